@@ -1,0 +1,87 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference modules
+(/root/reference/strhub/models/parseq/model.py under oracle/timm_shim.py) on seeded synthetic
+weights and crops.  Run in the build container (the GPU box has no /root/reference):
+
+    python -m oracle.make_golden
+
+TEST INFRASTRUCTURE ONLY.  Weights are not stored: they are regenerated from (experiment, seed) by
+parseq_b200.weights.init_state_dict and verified through `sd_digest`.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from parseq_b200.config import make_config                      # noqa: E402
+from parseq_b200.weights import init_state_dict, synth_images, state_dict_digest  # noqa: E402
+from oracle import reference_loader as RL                        # noqa: E402
+from oracle.parseq_oracle import ParseqOracle                    # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# (case name, experiment, weight seed, eos_bias, batch, image seed, decode_ar, refine_iters, max_length)
+CASES = [
+    ("s_ar1_b2",        "parseq",      0, 0.0, 2, 0, True,  1, None),
+    ("s_ar1_b1",        "parseq",      0, 0.0, 1, 7, True,  1, None),
+    ("s_ar0_b2",        "parseq",      0, 0.0, 2, 1, True,  0, None),
+    ("s_nar0_b2",       "parseq",      0, 0.0, 2, 2, False, 0, None),
+    ("s_nar3_b2",       "parseq",      0, 0.0, 2, 3, False, 3, None),
+    ("s_ar3_b2",        "parseq",      0, 0.0, 2, 4, True,  3, None),
+    ("s_ar1_len5_b2",   "parseq",      0, 0.0, 2, 5, True,  1, 5),
+    ("s_ar0_len1_b2",   "parseq",      0, 0.0, 2, 5, True,  0, 1),
+    ("s_eos_ar1_b4",    "parseq",      1, 0.5, 4, 6, True,  1, None),
+    ("s_eos_ar0_b4",    "parseq",      1, 0.7, 4, 6, True,  0, None),
+    ("s_eos_nar2_b4",   "parseq",      1, 0.5, 4, 8, False, 2, None),
+    ("ti_nar0_b1",      "parseq-tiny", 2, 0.0, 1, 9, False, 0, None),
+    ("ti_ar1_b3",       "parseq-tiny", 2, 0.0, 3, 10, True, 1, None),
+]
+
+
+def make_sd(experiment, seed, eos_bias):
+    cfg = make_config(experiment)
+    sd = init_state_dict(cfg, seed)
+    if eos_bias:
+        sd["head.bias"] = sd["head.bias"].clone()
+        sd["head.bias"][0] += eos_bias
+    return cfg, sd
+
+
+def main():
+    assert RL.available(), "reference tree not present"
+    os.makedirs(OUT, exist_ok=True)
+    cache = {}
+    for name, exp, wseed, eos_bias, B, iseed, ar, ri, ml in CASES:
+        key = (exp, wseed, eos_bias)
+        if key not in cache:
+            cfg, sd = make_sd(exp, wseed, eos_bias)
+            ref, tok = RL.build_reference_model(cfg, sd)
+            cache[key] = (cfg, sd, ref, tok, ParseqOracle(cfg, sd, "fp64"))
+        cfg, sd, ref, tok, o64 = cache[key]
+        x = synth_images(cfg, B, iseed)
+        ref.decode_ar, ref.refine_iters = ar, ri
+        with torch.inference_mode():
+            logits = ref(tok, x, ml).clone()
+            memory = ref.encode(x).clone()
+        o = o64.forward(x, ml, ar, ri)
+        assert o.logits.shape == logits.shape, (name, o.logits.shape, logits.shape)
+        err = (o.logits.float() - logits).abs().max().item()
+        blob = dict(
+            name=name, experiment=exp, weight_seed=wseed, eos_bias=eos_bias, batch=B, image_seed=iseed,
+            decode_ar=ar, refine_iters=ri, max_length=ml, sd_digest=state_dict_digest(sd),
+            logits=logits.contiguous(), memory0=memory[0].contiguous(),
+            min_margin_fp64=o.min_margin.float(), steps=o.steps,
+            source="reference strhub.models.parseq.model.PARSeq @ /root/reference (timm shim), torch %s CPU fp32"
+                   % torch.__version__,
+        )
+        torch.save(blob, os.path.join(OUT, name + ".pt"))
+        print(f"{name:18s} logits {tuple(logits.shape)} S={o.steps} |ref-fp64 oracle|={err:.2e} "
+              f"min margin {o.min_margin.min().item():.2e}")
+
+
+if __name__ == "__main__":
+    main()

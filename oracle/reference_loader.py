@@ -1,0 +1,52 @@
+"""Imports the reference's own `strhub.models.parseq.model.PARSeq` from /root/reference (read-only,
+present in the build container only) under the timm shim.  TEST INFRASTRUCTURE ONLY: used by
+oracle/make_golden.py and by CPU tests that are skipped when /root/reference is absent.
+
+Nothing in `-m gpu` tests, smoke() or bench.py calls this (the GPU box has no /root/reference).
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+REF_ROOT = os.environ.get("PARSEQ_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "strhub/models/parseq/model.py"))
+
+
+def load_reference_classes():
+    """Returns (RefPARSeqModel, RefTokenizer) imported from the reference tree.
+
+    The repo root also has a `strhub` package (the drop-in boundary); to import the REFERENCE one
+    its modules are loaded under the private alias `_refstrhub` by temporarily swapping sys.modules.
+    """
+    from . import timm_shim
+    timm_shim.install()
+    saved = {k: v for k, v in sys.modules.items() if k == "strhub" or k.startswith("strhub.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF_ROOT)
+    try:
+        model_mod = importlib.import_module("strhub.models.parseq.model")
+        data_mod = importlib.import_module("strhub.data.utils")
+        assert os.path.realpath(model_mod.__file__).startswith(os.path.realpath(REF_ROOT)), model_mod.__file__
+        Ref, Tok = model_mod.PARSeq, data_mod.Tokenizer
+    finally:
+        sys.path.remove(REF_ROOT)
+        for k in [k for k in sys.modules if k == "strhub" or k.startswith("strhub.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return Ref, Tok
+
+
+def build_reference_model(cfg, state_dict):
+    Ref, Tok = load_reference_classes()
+    tok = Tok(cfg.charset_train)
+    m = Ref(len(tok), cfg.max_label_length, list(cfg.img_size), list(cfg.patch_size), cfg.embed_dim,
+            cfg.enc_num_heads, cfg.enc_mlp_ratio, cfg.enc_depth, cfg.dec_num_heads, cfg.dec_mlp_ratio,
+            cfg.dec_depth, cfg.decode_ar, cfg.refine_iters, cfg.dropout)
+    missing, unexpected = m.load_state_dict(state_dict, strict=True), None
+    return m.eval(), tok
