@@ -1,0 +1,129 @@
+/*
+ * parseq_b200.h - C ABI of the B200-native PARSeq inference engine (libparseq_b200.so).
+ *
+ * The reference (baudm/parseq) has no FFI / plugin boundary for this path: it sits behind the Python
+ * class strhub.models.parseq.system.PARSeq (system.py:33-88) wrapping the nn.Module
+ * strhub.models.parseq.model.PARSeq (model.py:31-169).  Each entry point below states the reference
+ * method it replaces.  All pointers are plain device or host pointers; no torch types cross this
+ * boundary.  All functions return 0 on success and a negative parseq_status on failure;
+ * parseq_last_error() returns a human-readable message for the calling thread's last failure.
+ *
+ * Threading / streams: an engine handle is NOT thread-safe (one handle per device and stream user).
+ * All work is enqueued on the caller's stream; the only host synchronisation is inside
+ * parseq_forward_host (which must return host-visible results) and parseq_finalize.
+ */
+#ifndef PARSEQ_B200_H_
+#define PARSEQ_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct parseq_engine parseq_engine;
+typedef void* parseq_stream_t;           /* cudaStream_t */
+
+typedef enum parseq_status {
+  PARSEQ_OK = 0,
+  PARSEQ_ERR_INVALID_ARG = -1,
+  PARSEQ_ERR_UNSUPPORTED = -2,           /* configuration outside what the kernels cover */
+  PARSEQ_ERR_CUDA = -3,
+  PARSEQ_ERR_STATE = -4,                 /* e.g. forward before finalize, missing weight */
+  PARSEQ_ERR_NO_DEVICE = -5              /* no sm_100 device: there is NO CPU fallback */
+} parseq_status;
+
+/* Architecture hyper-parameters: the ctor arguments of model.PARSeq (model.py:33-49) /
+ * system.PARSeq (system.py:35-60).  num_tokens = len(tokenizer) = charset + EOS + BOS + PAD. */
+typedef struct parseq_config {
+  int32_t img_h, img_w;                  /* img_size     */
+  int32_t patch_h, patch_w;              /* patch_size   */
+  int32_t embed_dim;
+  int32_t enc_num_heads, enc_mlp_ratio, enc_depth;
+  int32_t dec_num_heads, dec_mlp_ratio, dec_depth;   /* dec_depth must be 1 (all reference configs) */
+  int32_t max_label_length;              /* 25 -> 26 decode positions */
+  int32_t num_tokens;                    /* 97: EOS=0, chars 1..94, BOS=95, PAD=96 (data/utils.py:102-111) */
+  int32_t max_batch;                     /* images processed per internal chunk (workspace sizing); 0 = default */
+  int32_t device;                        /* CUDA device ordinal */
+} parseq_config;
+
+/* Replaces model.PARSeq.__init__ (model.py:33-71): allocates device weights + workspace. */
+int parseq_create(const parseq_config* cfg, parseq_engine** out);
+void parseq_destroy(parseq_engine* e);
+
+/* Replaces model.PARSeq.load_state_dict as used by strhub/models/utils.py:80-82: `key` is a
+ * state_dict key of the inner model (e.g. "encoder.blocks.3.attn.qkv.weight",
+ * "decoder.layers.0.cross_attn.in_proj_weight", "pos_queries"); `data` is a HOST pointer to `numel`
+ * contiguous fp32 values in PyTorch layout.  GEMM weight matrices are rounded to bf16 on upload. */
+int parseq_set_weight(parseq_engine* e, const char* key, const float* data, int64_t numel);
+/* Number of state_dict keys the engine expects, and the i-th key / its element count. */
+int parseq_num_weights(const parseq_engine* e);
+const char* parseq_weight_key(const parseq_engine* e, int i, int64_t* numel);
+
+/* Input-independent precomputation (content K/V table over (position, token), query projections
+ * of pos_queries); must be called after all weights are set and after any weight update. */
+int parseq_finalize(parseq_engine* e, parseq_stream_t stream);
+
+/* Decode options of one forward call: model.PARSeq.forward(tokenizer, images, max_length)
+ * (model.py:105-169) with the module attributes decode_ar / refine_iters (model.py:55-56). */
+typedef struct parseq_forward_args {
+  int32_t batch;                         /* N images */
+  int32_t max_length;                    /* -1 = None ("testing": early-exit length reported in *steps) */
+  int32_t decode_ar;                     /* 0 / 1 */
+  int32_t refine_iters;
+  /* Optional teacher forcing (debug / parity): device int32 [batch, num_steps]; AR step i feeds
+   * forced_ids[:, i+1] instead of its own argmax.  NULL in production. */
+  const int32_t* forced_ids;
+  /* Optional: device int32 [refine_iters, batch, num_steps] contexts (BOS included) for the cloze passes. */
+  const int32_t* forced_refine;
+} parseq_forward_args;
+
+/* Replaces system.PARSeq.forward -> model.PARSeq.forward (system.py:87-88, model.py:105-169).
+ *   images : DEVICE fp32 [N,3,H,W] (NCHW, values as produced by T.Normalize(0.5,0.5))
+ *   logits : DEVICE fp32 [N, num_steps, num_tokens-2], num_steps = min(max_length,25)+1 (26 if -1)
+ *   ids    : DEVICE int32 [N, num_steps] argmax of `logits` (may be NULL)
+ *   steps  : DEVICE int32 [1] (may be NULL): S = number of AR steps the reference would have run
+ *            before its batch-wide early exit (model.py:144); == num_steps when max_length >= 0,
+ *            when decode_ar == 0.  Only affects the returned SHAPE when refine_iters == 0. */
+int parseq_forward(parseq_engine* e, const parseq_forward_args* args, const float* images,
+                   float* logits, int32_t* ids, int32_t* steps, parseq_stream_t stream);
+
+/* End-to-end variant with HOST buffers (pinned or pageable): H2D of images, forward, D2H of
+ * logits / ids / steps, synchronised on return.  This is what bench.py times as `e2e`. */
+int parseq_forward_host(parseq_engine* e, const parseq_forward_args* args, const float* images_host,
+                        float* logits_host, int32_t* ids_host, int32_t* steps_host,
+                        parseq_stream_t stream);
+
+/* Replaces model.PARSeq.encode (model.py:83-84): memory DEVICE fp32 [N, T, D]. */
+int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* memory,
+                  parseq_stream_t stream);
+
+/* Introspection used by bench.py / tests. */
+int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count of kernels launched */
+/* Options: "chunk" (images per internal chunk), "timing" (1: record a CUDA-event pair around every launch
+ * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests). */
+int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
+/* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of
+ * category 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other. */
+int parseq_get_timing(parseq_engine* e, int category, double* ms, double* flops, int64_t* count);
+const char* parseq_last_error(void);
+const char* parseq_version(void);
+
+/* Stand-alone kernel entry points (unit tests of the building blocks; all pointers DEVICE). */
+/* C[M,N] = epilogue(A[M,K](bf16,row-major,lda) * W[N,K]^T(bf16,row-major,ldw) + bias) on tcgen05.
+ * mode: 0 -> fp32 out (alpha*(acc+bias) [+ resid[row % resid_mod or row]]), 1 -> bf16 out,
+ *       2 -> bf16 gelu(acc+bias). */
+int parseq_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                     int M, int N, int K, int mode, float alpha, const float* resid, int64_t ldr,
+                     int resid_mod, void* out, int64_t ldo, parseq_stream_t stream);
+/* y = bf16(LayerNorm(x; gamma, beta, eps)), x fp32 [M, D]. */
+int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M,
+                          int D, void* y_bf16, float* y_f32_or_null, parseq_stream_t stream);
+/* out[B*T, D] = softmax(QK^T/sqrt(64)) V per (image, head) from packed qkv bf16 [B*T, 3D]. */
+int parseq_enc_attention(const void* qkv_bf16, int B, int T, int D, int heads, void* out_bf16,
+                         parseq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARSEQ_B200_H_ */

@@ -70,11 +70,15 @@ def main():
         o = o64.forward(x, ml, ar, ri)
         assert o.logits.shape == logits.shape, (name, o.logits.shape, logits.shape)
         err = (o.logits.float() - logits).abs().max().item()
+        assert err < 1e-5, (name, err)          # pins the oracle (and its id trajectory) to the reference
         blob = dict(
             name=name, experiment=exp, weight_seed=wseed, eos_bias=eos_bias, batch=B, image_seed=iseed,
             decode_ar=ar, refine_iters=ri, max_length=ml, sd_digest=state_dict_digest(sd),
             logits=logits.contiguous(), memory0=memory[0].contiguous(),
             min_margin_fp64=o.min_margin.float(), steps=o.steps,
+            # id trajectory of the reference run (for teacher-forced logit comparisons)
+            ar_ids=None if o.ar_ids is None else o.ar_ids.int(),
+            refine_ctx=[c.int() for c in o.refine_ctx],
             source="reference strhub.models.parseq.model.PARSeq @ /root/reference (timm shim), torch %s CPU fp32"
                    % torch.__version__,
         )
@@ -83,5 +87,41 @@ def main():
               f"min margin {o.min_margin.min().item():.2e}")
 
 
+def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau):
+    """Margin-filtered free-running set: candidates whose smallest top1-top2 margin over
+    every argmax decision of the fp32 reference run exceeds `tau`; on these, decoded ids must be bit-identical
+    between the bf16 engine and the fp32 reference."""
+    cfg, sd = make_sd(exp, wseed, 0.0)
+    ref, tok = RL.build_reference_model(cfg, sd)
+    ref.decode_ar, ref.refine_iters = ar, ri
+    o32 = ParseqOracle(cfg, sd, "fp32")
+    picks, ids, logits, margins, n_cand = [], [], [], [], 0
+    for blk in range(n_blocks):
+        seed = 90_000 + blk
+        x = synth_images(cfg, block, seed)
+        o = o32.forward(x, ml, ar, ri)
+        n_cand += block
+        keep = torch.nonzero(o.min_margin > tau).flatten().tolist()
+        if keep:
+            with torch.inference_mode():
+                lr = ref(tok, x[keep], ml)          # the reference itself on the accepted images
+            assert (lr - o.logits[keep]).abs().max().item() < 1e-5
+            for j, k in enumerate(keep):
+                picks.append((seed, k)); ids.append(lr[j].argmax(-1).int()); logits.append(lr[j].clone())
+                margins.append(float(o.min_margin[k]))
+        print(f"{name}: block {blk + 1}/{n_blocks} accepted so far {len(picks)}/{n_cand}", flush=True)
+    blob = dict(name=name, experiment=exp, weight_seed=wseed, decode_ar=ar, refine_iters=ri, max_length=ml,
+                block=block, tau=tau, candidates=n_cand, picks=picks, ids=torch.stack(ids),
+                logits=torch.stack(logits), margins=torch.tensor(margins), sd_digest=state_dict_digest(sd))
+    torch.save(blob, os.path.join(OUT, name + ".pt"))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "filtered_ti":
+        make_filtered("filtered_ti_ar1_len5", "parseq-tiny", 2, True, 1, 5, 4, 256, 0.012)
+    elif len(sys.argv) > 1 and sys.argv[1] == "filtered":
+        make_filtered("filtered_s_ar1", "parseq", 0, True, 1, None, 16, 256, 0.02)
+        make_filtered("filtered_s_ar1_len5", "parseq", 0, True, 1, 5, 2, 256, 0.02)
+        make_filtered("filtered_ti_ar1_len5", "parseq-tiny", 2, True, 1, 5, 4, 256, 0.012)
+    else:
+        main()

@@ -1,0 +1,744 @@
+// libparseq_b200.so: host-side engine + C ABI (include/parseq_b200.h) of the B200-native PARSeq
+// inference path.  Restates, as a fixed kernel schedule on one CUDA stream, what
+// strhub/models/parseq/model.py:105-169 (PARSeq.forward: encode, AR loop, NAR, cloze refinement)
+// does through nn.Module calls.  There is no CPU path: without an sm_100 device creation fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/parseq_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define PQ_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(PARSEQ_ERR_CUDA, std::string(#expr) + " -> " + cudaGetErrorString(_e));          \
+  } while (0)
+#define PQ_TRY(expr)                 \
+  do {                               \
+    int _r = (expr);                 \
+    if (_r != PARSEQ_OK) return _r;  \
+  } while (0)
+
+// ---------------------------------------------------------------- driver entry point for TMA descriptors
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+int load_driver_api() {
+  if (g_encode != nullptr) return PARSEQ_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+    return fail(PARSEQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return PARSEQ_OK;
+}
+
+// 2D bf16 tensor map: rows x cols (cols contiguous), row stride ld elements, box = box_rows x 64 cols, 128B swizzle.
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  PQ_TRY(load_driver_api());
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ((ld * 2) & 15) != 0)
+    return fail(PARSEQ_ERR_INVALID_ARG, "GEMM operand must be 16-byte aligned with a 16-byte multiple row stride");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(pq::GEMM_BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PARSEQ_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return PARSEQ_OK;
+}
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+int g_sm_count = 0;
+bool g_attr_set[3] = {false, false, false};
+
+template <int BN>
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const pq::GemmParams& p, int grid, cudaStream_t st,
+                   int slot) {
+  auto kern = pq::gemm_bf16_tcgen05_kernel<BN>;
+  if (!g_attr_set[slot]) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<BN>::kSmemBytes));
+    g_attr_set[slot] = true;
+  }
+  kern<<<grid, pq::GEMM_THREADS, pq::GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  PQ_CUDA(cudaGetLastError());
+  return PARSEQ_OK;
+}
+
+int g_block_n_override = 0;
+
+int gemm_launch(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
+                int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
+                cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm: empty problem");
+  if (g_sm_count == 0) {
+    int dev = 0;
+    PQ_CUDA(cudaGetDevice(&dev));
+    PQ_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int BN = 128;
+  if (g_block_n_override) BN = g_block_n_override;
+  else if (N % 256 == 0 && static_cast<long long>((M + 127) / 128) * (N / 256) >= 2ll * g_sm_count) BN = 256;
+  else if (N <= 64) BN = 64;
+  CUtensorMap ta, tb;
+  PQ_TRY(make_tmap_bf16(&ta, A, M, K, lda, pq::GEMM_BLOCK_M));
+  PQ_TRY(make_tmap_bf16(&tb, W, N, K, ldw, BN));
+  pq::GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.mode = mode; p.alpha = alpha; p.bias = bias;
+  p.resid = resid; p.ldr = ldr; p.resid_mod = resid_mod; p.out = out; p.ldo = ldo;
+  const int esz = (mode == pq::EPI_F32) ? 4 : 2;
+  bool vec = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((ldo * esz) % 16 == 0);
+  if (resid != nullptr) vec = vec && ((reinterpret_cast<uintptr_t>(resid) & 15u) == 0) && ((ldr * 4) % 16 == 0);
+  if (bias != nullptr) vec = vec && ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0);
+  p.vec_ok = vec ? 1 : 0;
+  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
+  p.num_n_tiles = (N + BN - 1) / BN;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+  if (BN == 256) return launch_gemm_bn<256>(ta, tb, p, grid, st, 2);
+  if (BN == 64) return launch_gemm_bn<64>(ta, tb, p, grid, st, 0);
+  return launch_gemm_bn<128>(ta, tb, p, grid, st, 1);
+}
+
+int layernorm_launch(const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
+                     cudaStream_t st) {
+  const int rows_per_block = 8;
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (D) {
+    case 192: pq::layernorm_kernel<192><<<grid, 256, 0, st>>>(x, g, b, eps, M, yb, y32); break;
+    case 384: pq::layernorm_kernel<384><<<grid, 256, 0, st>>>(x, g, b, eps, M, yb, y32); break;
+    case 768: pq::layernorm_kernel<768><<<grid, 256, 0, st>>>(x, g, b, eps, M, yb, y32); break;
+    default: return fail(PARSEQ_ERR_UNSUPPORTED, "layernorm: embed_dim must be 192, 384 or 768");
+  }
+  PQ_CUDA(cudaGetLastError());
+  return PARSEQ_OK;
+}
+
+int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
+  if (T != pq::ATT_T || D != heads * pq::ATT_DH)
+    return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernel covers T=128 tokens, head_dim=64");
+  pq::enc_attention_kernel<<<B * heads, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                      reinterpret_cast<__nv_bfloat16*>(out), D, heads);
+  PQ_CUDA(cudaGetLastError());
+  return PARSEQ_OK;
+}
+
+struct Slot {
+  std::string key;
+  long long numel;
+  bool bf16;
+  void* dev;
+  bool set;
+};
+
+}  // namespace
+
+struct parseq_engine {
+  parseq_config cfg;
+  int D, T, Kp, Me, Md, L, V, C, gh, gw, dh_dec;
+  int chunk;
+  std::vector<Slot> slots;
+  std::map<std::string, int> index;
+  bool finalized = false;
+  long long launches = 0;
+  // optional per-category device timing (bench.py roofline pass; off on the throughput pass)
+  bool timing = false;
+  struct TimedLaunch { int cat; double flops; cudaEvent_t a, b; };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
+  int cur_cat = 5;
+  // derived tables
+  __nv_bfloat16* kvtab = nullptr;   // [L*V, 2D]
+  float* qs = nullptr;              // [L, D]
+  // workspace (chunk images)
+  __nv_bfloat16 *a_pe = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *mem = nullptr,
+                *ckv = nullptr;
+  float* x = nullptr;
+  __nv_bfloat16 *sa = nullptr, *yn = nullptr, *ca = nullptr, *hd = nullptr;
+  float *y = nullptr, *qc = nullptr;
+  int *ids_ar = nullptr, *ids_ctx = nullptr;
+  // host-API staging
+  float* st_images = nullptr; float* st_logits = nullptr; int* st_ids = nullptr; int* st_steps = nullptr;
+  long long st_batch = 0;
+
+  void* w(const std::string& k) const { return slots[index.at(k)].dev; }
+  const float* wf(const std::string& k) const { return reinterpret_cast<const float*>(w(k)); }
+  const __nv_bfloat16* wb(const std::string& k) const { return reinterpret_cast<const __nv_bfloat16*>(w(k)); }
+};
+
+namespace {
+
+void add_slot(parseq_engine* e, const std::string& key, long long numel, bool bf16) {
+  e->index[key] = static_cast<int>(e->slots.size());
+  e->slots.push_back(Slot{key, numel, bf16, nullptr, false});
+}
+
+template <typename Tp>
+int dev_alloc(Tp** p, long long n) {
+  PQ_CUDA(cudaMalloc(reinterpret_cast<void**>(p), static_cast<size_t>(n) * sizeof(Tp)));
+  return PARSEQ_OK;
+}
+
+int alloc_workspace(parseq_engine* e) {
+  const long long R = static_cast<long long>(e->chunk) * e->T;
+  const long long Rd = static_cast<long long>(e->chunk) * e->L;
+  const int D = e->D;
+  PQ_TRY(dev_alloc(&e->a_pe, R * e->Kp));
+  PQ_TRY(dev_alloc(&e->x, R * D));
+  PQ_TRY(dev_alloc(&e->xn, R * D));
+  PQ_TRY(dev_alloc(&e->qkv, R * 3 * D));
+  PQ_TRY(dev_alloc(&e->att, R * D));
+  PQ_TRY(dev_alloc(&e->hid, R * e->Me));
+  PQ_TRY(dev_alloc(&e->mem, R * D));
+  PQ_TRY(dev_alloc(&e->ckv, R * 2 * D));
+  PQ_TRY(dev_alloc(&e->sa, Rd * D));
+  PQ_TRY(dev_alloc(&e->yn, Rd * D));
+  PQ_TRY(dev_alloc(&e->ca, Rd * D));
+  PQ_TRY(dev_alloc(&e->hd, Rd * e->Md));
+  PQ_TRY(dev_alloc(&e->y, Rd * D));
+  PQ_TRY(dev_alloc(&e->qc, Rd * D));
+  PQ_TRY(dev_alloc(&e->ids_ar, static_cast<long long>(e->chunk) * 32));
+  PQ_TRY(dev_alloc(&e->ids_ctx, static_cast<long long>(e->chunk) * 32));
+  return PARSEQ_OK;
+}
+
+void free_workspace(parseq_engine* e) {
+  void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->mem, e->ckv, e->sa, e->yn, e->ca,
+                  e->hd, e->y, e->qc, e->ids_ar, e->ids_ctx};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  e->a_pe = e->xn = e->qkv = e->att = e->hid = e->mem = e->ckv = e->sa = e->yn = e->ca = e->hd = nullptr;
+  e->x = e->y = e->qc = nullptr;
+  e->ids_ar = e->ids_ctx = nullptr;
+}
+
+// categories: 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other
+enum { CAT_ENC_GEMM = 0, CAT_ENC_ATTN = 1, CAT_LN = 2, CAT_DEC_GEMM = 3, CAT_DEC_ATTN = 4, CAT_MISC = 5, CAT_COUNT = 6 };
+
+cudaEvent_t pool_event(parseq_engine* e) {
+  if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
+  cudaEvent_t ev; cudaEventCreate(&ev); return ev;
+}
+struct TimedScope {   // records a CUDA-event pair around the launches issued in its lifetime
+  parseq_engine* e; cudaStream_t st; int idx = -1;
+  TimedScope(parseq_engine* e_, cudaStream_t st_, int cat, double flops) : e(e_), st(st_) {
+    e->launches++;
+    if (!e->timing) return;
+    parseq_engine::TimedLaunch t{cat, flops, pool_event(e), pool_event(e)};
+    cudaEventRecord(t.a, st);
+    e->timed.push_back(t);
+    idx = static_cast<int>(e->timed.size()) - 1;
+  }
+  ~TimedScope() { if (idx >= 0) cudaEventRecord(e->timed[idx].b, st); }
+};
+
+int gemm(parseq_engine* e, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N,
+         int K, int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
+         cudaStream_t st) {
+  TimedScope ts(e, st, e->cur_cat == CAT_DEC_GEMM ? CAT_DEC_GEMM : CAT_ENC_GEMM, 2.0 * M * N * K);
+  return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st);
+}
+int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float eps, int M, void* y, float* y32,
+              cudaStream_t st) {
+  TimedScope ts(e, st, CAT_LN, 0.0);
+  return layernorm_launch(x, e->wf(prefix + ".weight"), e->wf(prefix + ".bias"), eps, M, e->D, y, y32, st);
+}
+
+// ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
+int encode_chunk(parseq_engine* e, const float* images, int B, float* memory32, cudaStream_t st) {
+  const int D = e->D, T = e->T, M = B * T;
+  e->cur_cat = CAT_ENC_GEMM;
+  {
+    TimedScope ts(e, st, CAT_MISC, 0.0);
+    const long long total = static_cast<long long>(B) * e->gh * e->gw * 3 * e->cfg.patch_h;
+    const int grid = static_cast<int>((total + 255) / 256);
+    pq::im2col_patch_kernel<<<grid, 256, 0, st>>>(images, e->a_pe, B, e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h,
+                                                  e->cfg.patch_w, e->gh, e->gw);
+    PQ_CUDA(cudaGetLastError());
+  }
+  // x = patches * Wpe^T + bpe + pos_embed
+  PQ_TRY(gemm(e, e->a_pe, e->Kp, e->w("encoder.patch_embed.proj.weight"), e->Kp,
+              e->wf("encoder.patch_embed.proj.bias"), M, D, e->Kp, pq::EPI_F32, 1.0f, e->wf("encoder.pos_embed"), D, T,
+              e->x, D, st));
+  for (int i = 0; i < e->cfg.enc_depth; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+    PQ_TRY(layernorm(e, e->x, p + "norm1", 1e-6f, M, e->xn, nullptr, st));
+    PQ_TRY(gemm(e, e->xn, D, e->w(p + "attn.qkv.weight"), D, e->wf(p + "attn.qkv.bias"), M, 3 * D, D, pq::EPI_BF16,
+                1.0f, nullptr, 0, 0, e->qkv, 3 * D, st));
+    {
+      TimedScope ts(e, st, CAT_ENC_ATTN, 4.0 * B * T * T * D);
+      PQ_TRY(enc_attention_launch(e->qkv, B, T, D, e->cfg.enc_num_heads, e->att, st));
+    }
+    PQ_TRY(gemm(e, e->att, D, e->w(p + "attn.proj.weight"), D, e->wf(p + "attn.proj.bias"), M, D, D, pq::EPI_F32, 1.0f,
+                e->x, D, 0, e->x, D, st));
+    PQ_TRY(layernorm(e, e->x, p + "norm2", 1e-6f, M, e->xn, nullptr, st));
+    PQ_TRY(gemm(e, e->xn, D, e->w(p + "mlp.fc1.weight"), D, e->wf(p + "mlp.fc1.bias"), M, e->Me, D, pq::EPI_GELU_BF16,
+                1.0f, nullptr, 0, 0, e->hid, e->Me, st));
+    PQ_TRY(gemm(e, e->hid, e->Me, e->w(p + "mlp.fc2.weight"), e->Me, e->wf(p + "mlp.fc2.bias"), M, D, e->Me,
+                pq::EPI_F32, 1.0f, e->x, D, 0, e->x, D, st));
+  }
+  PQ_TRY(layernorm(e, e->x, "encoder.norm", 1e-6f, M, e->mem, memory32, st));
+  return PARSEQ_OK;
+}
+
+// ---------------------------------------------------------------- one Decoder call (model.py:86-103, modules.py:55-125)
+// rows are (b, qi), qi in [0,nq); query position q0+qi; context ids[b, 0..nkeys-1].
+int decode_pass(parseq_engine* e, int B, int nq, int q0, int nkeys, int mode, const int* ids, float* logits_out,
+                long long logits_ld, cudaStream_t st) {
+  const int D = e->D, M = B * nq;
+  const std::string Ly = "decoder.layers.0.";
+  const float qscale = 1.0f / std::sqrt(static_cast<float>(e->dh_dec));
+  const __nv_bfloat16* Wc = e->wb(Ly + "cross_attn.in_proj_weight");
+  const float* bc = e->wf(Ly + "cross_attn.in_proj_bias");
+  e->cur_cat = CAT_DEC_GEMM;
+  {
+    TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
+    pq::dec_self_attn_kernel<<<M, D, 0, st>>>(e->qs, e->kvtab, ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, e->sa);
+    PQ_CUDA(cudaGetLastError());
+  }
+  const float* posq = e->wf("pos_queries") + static_cast<long long>(q0) * D;
+  PQ_TRY(gemm(e, e->sa, D, e->w(Ly + "self_attn.out_proj.weight"), D, e->wf(Ly + "self_attn.out_proj.bias"), M, D, D,
+              pq::EPI_F32, 1.0f, posq, D, nq, e->y, D, st));
+  PQ_TRY(layernorm(e, e->y, Ly + "norm1", 1e-5f, M, e->yn, nullptr, st));
+  PQ_TRY(gemm(e, e->yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, e->qc, D, st));
+  {
+    TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
+    const int heads = e->cfg.dec_num_heads;
+    if (e->T <= 128) {
+      const size_t sm = static_cast<size_t>(heads) * (32 + 128) * sizeof(float);
+      pq::dec_cross_attn_kernel<128><<<M, D, sm, st>>>(e->qc, e->ckv, e->T, D, nq, e->ca);
+    } else {
+      const size_t sm = static_cast<size_t>(heads) * (32 + 256) * sizeof(float);
+      pq::dec_cross_attn_kernel<256><<<M, D, sm, st>>>(e->qc, e->ckv, e->T, D, nq, e->ca);
+    }
+    PQ_CUDA(cudaGetLastError());
+  }
+  PQ_TRY(gemm(e, e->ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
+              pq::EPI_F32, 1.0f, e->y, D, 0, e->y, D, st));
+  PQ_TRY(layernorm(e, e->y, Ly + "norm2", 1e-5f, M, e->yn, nullptr, st));
+  PQ_TRY(gemm(e, e->yn, D, e->w(Ly + "linear1.weight"), D, e->wf(Ly + "linear1.bias"), M, e->Md, D, pq::EPI_GELU_BF16,
+              1.0f, nullptr, 0, 0, e->hd, e->Md, st));
+  PQ_TRY(gemm(e, e->hd, e->Md, e->w(Ly + "linear2.weight"), e->Md, e->wf(Ly + "linear2.bias"), M, D, e->Md, pq::EPI_F32,
+              1.0f, e->y, D, 0, e->y, D, st));
+  PQ_TRY(layernorm(e, e->y, "decoder.norm", 1e-5f, M, e->yn, nullptr, st));
+  PQ_TRY(gemm(e, e->yn, D, e->w("head.weight"), D, e->wf("head.bias"), M, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0,
+              logits_out, logits_ld, st));
+  return PARSEQ_OK;
+}
+
+int argmax_rows(parseq_engine* e, const float* logits, int L, int B, int nrows, int src0, int* ids, int ids_ld, int dst0,
+                const int* forced, int forced_ld, cudaStream_t st) {
+  const int warps = B * nrows;
+  if (warps <= 0) return PARSEQ_OK;
+  TimedScope ts(e, st, CAT_MISC, 0.0);
+  pq::argmax_rows_kernel<<<(warps + 7) / 8, 256, 0, st>>>(logits, L, e->C, B, nrows, src0, ids, ids_ld, dst0, forced,
+                                                          forced_ld);
+  PQ_CUDA(cudaGetLastError());
+  return PARSEQ_OK;
+}
+
+int forward_chunk(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const float* images,
+                  float* logits, int* ids_out, int* steps, cudaStream_t st) {
+  const int D = e->D, T = e->T, C = e->C;
+  const int bos = e->V - 2, pad = e->V - 1;
+  const bool testing = a->max_length < 0;
+  PQ_TRY(encode_chunk(e, images, B, nullptr, st));
+  // cross-attention K/V of the image memory, once per image (reference recomputes it in every decode call)
+  e->cur_cat = CAT_DEC_GEMM;
+  {
+    const std::string Ly = "decoder.layers.0.";
+    const __nv_bfloat16* Wkv = e->wb(Ly + "cross_attn.in_proj_weight") + static_cast<long long>(D) * D;
+    const float* bkv = e->wf(Ly + "cross_attn.in_proj_bias") + D;
+    PQ_TRY(gemm(e, e->mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, e->ckv, 2 * D, st));
+  }
+  const long long LC = static_cast<long long>(L) * C;
+  if (a->decode_ar) {
+    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->ids_ar, B, 32, bos, pad);
+    PQ_CUDA(cudaGetLastError());
+    e->launches++;
+    const int* forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
+    for (int i = 0; i < L; ++i) {
+      PQ_TRY(decode_pass(e, B, 1, i, i + 1, 0, e->ids_ar, logits + static_cast<long long>(i) * C, LC, st));
+      if (i + 1 < L) PQ_TRY(argmax_rows(e, logits, L, B, 1, i, e->ids_ar, 32, i + 1, forced, L, st));
+    }
+    if (testing && steps != nullptr) {
+      pq::ar_steps_kernel<<<1, 256, 0, st>>>(e->ids_ar, 32, B, L, 0, steps);
+      PQ_CUDA(cudaGetLastError());
+      e->launches++;
+    }
+  } else {
+    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->ids_ctx, B, 32, bos, pad);
+    PQ_CUDA(cudaGetLastError());
+    e->launches++;
+    PQ_TRY(decode_pass(e, B, L, 0, 1, 0, e->ids_ctx, logits, C, st));
+  }
+  for (int it = 0; it < a->refine_iters; ++it) {
+    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->ids_ctx, B, 32, bos, pad);
+    PQ_CUDA(cudaGetLastError());
+    e->launches++;
+    const int* forced = a->forced_refine
+                            ? a->forced_refine + (static_cast<long long>(it) * a->batch + b0) * L
+                            : nullptr;
+    // ctx = [BOS, argmax(logits[:, :L-1])]  (model.py:161)
+    PQ_TRY(argmax_rows(e, logits, L, B, L - 1, 0, e->ids_ctx, 32, 1, forced, L, st));
+    PQ_TRY(decode_pass(e, B, L, 0, L, 1, e->ids_ctx, logits, C, st));
+  }
+  if (ids_out != nullptr) PQ_TRY(argmax_rows(e, logits, L, B, L, 0, ids_out, L, 0, nullptr, 0, st));
+  return PARSEQ_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* parseq_last_error(void) { return g_last_error.c_str(); }
+const char* parseq_version(void) { return "parseq_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+
+int parseq_create(const parseq_config* cfg, parseq_engine** out) {
+  if (cfg == nullptr || out == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PARSEQ_ERR_NO_DEVICE, "no CUDA device: parseq_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PARSEQ_ERR_INVALID_ARG, "bad device ordinal");
+  PQ_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  PQ_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(PARSEQ_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                          ", the kernels are sm_100a (B200) only");
+  g_sm_count = prop.multiProcessorCount;
+  if (cfg->dec_depth != 1) return fail(PARSEQ_ERR_UNSUPPORTED, "dec_depth must be 1");
+  if (cfg->img_h % cfg->patch_h || cfg->img_w % cfg->patch_w) return fail(PARSEQ_ERR_INVALID_ARG, "img/patch mismatch");
+  const int D = cfg->embed_dim;
+  if (D != 192 && D != 384 && D != 768) return fail(PARSEQ_ERR_UNSUPPORTED, "embed_dim must be 192, 384 or 768");
+  if (D != cfg->enc_num_heads * 64) return fail(PARSEQ_ERR_UNSUPPORTED, "encoder head_dim must be 64");
+  if (D != cfg->dec_num_heads * 32) return fail(PARSEQ_ERR_UNSUPPORTED, "decoder head_dim must be 32");
+  if (cfg->max_label_length + 1 > 32) return fail(PARSEQ_ERR_UNSUPPORTED, "max_label_length must be <= 31");
+  auto* e = new parseq_engine();
+  e->cfg = *cfg;
+  e->D = D;
+  e->gh = cfg->img_h / cfg->patch_h;
+  e->gw = cfg->img_w / cfg->patch_w;
+  e->T = e->gh * e->gw;
+  e->Kp = 3 * cfg->patch_h * cfg->patch_w;
+  e->Me = D * cfg->enc_mlp_ratio;
+  e->Md = D * cfg->dec_mlp_ratio;
+  e->L = cfg->max_label_length + 1;
+  e->V = cfg->num_tokens;
+  e->C = cfg->num_tokens - 2;
+  e->dh_dec = D / cfg->dec_num_heads;
+  e->chunk = cfg->max_batch > 0 ? cfg->max_batch : 128;
+  if (e->T != 128) {
+    delete e;
+    return fail(PARSEQ_ERR_UNSUPPORTED, "this build covers 128-token images (32x128 / patch 4x8)");
+  }
+  if ((e->Kp * 2) % 16 != 0) { delete e; return fail(PARSEQ_ERR_UNSUPPORTED, "patch dim must be a multiple of 8"); }
+  // ---- weight slots: state_dict keys of strhub.models.parseq.model.PARSeq ----
+  add_slot(e, "encoder.pos_embed", 1ll * e->T * D, false);
+  add_slot(e, "encoder.patch_embed.proj.weight", 1ll * D * e->Kp, true);
+  add_slot(e, "encoder.patch_embed.proj.bias", D, false);
+  for (int i = 0; i < cfg->enc_depth; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+    add_slot(e, p + "norm1.weight", D, false);
+    add_slot(e, p + "norm1.bias", D, false);
+    add_slot(e, p + "attn.qkv.weight", 3ll * D * D, true);
+    add_slot(e, p + "attn.qkv.bias", 3 * D, false);
+    add_slot(e, p + "attn.proj.weight", 1ll * D * D, true);
+    add_slot(e, p + "attn.proj.bias", D, false);
+    add_slot(e, p + "norm2.weight", D, false);
+    add_slot(e, p + "norm2.bias", D, false);
+    add_slot(e, p + "mlp.fc1.weight", 1ll * e->Me * D, true);
+    add_slot(e, p + "mlp.fc1.bias", e->Me, false);
+    add_slot(e, p + "mlp.fc2.weight", 1ll * D * e->Me, true);
+    add_slot(e, p + "mlp.fc2.bias", D, false);
+  }
+  add_slot(e, "encoder.norm.weight", D, false);
+  add_slot(e, "encoder.norm.bias", D, false);
+  const std::string Ly = "decoder.layers.0.";
+  for (const char* att : {"self_attn", "cross_attn"}) {
+    add_slot(e, Ly + att + ".in_proj_weight", 3ll * D * D, true);
+    add_slot(e, Ly + att + ".in_proj_bias", 3 * D, false);
+    add_slot(e, Ly + att + ".out_proj.weight", 1ll * D * D, true);
+    add_slot(e, Ly + att + ".out_proj.bias", D, false);
+  }
+  add_slot(e, Ly + "linear1.weight", 1ll * e->Md * D, true);
+  add_slot(e, Ly + "linear1.bias", e->Md, false);
+  add_slot(e, Ly + "linear2.weight", 1ll * D * e->Md, true);
+  add_slot(e, Ly + "linear2.bias", D, false);
+  for (const char* n : {"norm1", "norm2", "norm_q", "norm_c"}) {
+    add_slot(e, Ly + n + ".weight", D, false);
+    add_slot(e, Ly + n + ".bias", D, false);
+  }
+  add_slot(e, "decoder.norm.weight", D, false);
+  add_slot(e, "decoder.norm.bias", D, false);
+  add_slot(e, "head.weight", 1ll * e->C * D, true);
+  add_slot(e, "head.bias", e->C, false);
+  add_slot(e, "text_embed.embedding.weight", 1ll * e->V * D, false);
+  add_slot(e, "pos_queries", 1ll * e->L * D, false);
+  for (auto& s : e->slots) {
+    // +64 elements of slack: head.bias (95 floats) is read with float4 only when in range, but keep
+    // every buffer 16-byte padded
+    const size_t bytes = static_cast<size_t>(s.numel + 64) * (s.bf16 ? 2 : 4);
+    if (cudaMalloc(&s.dev, bytes) != cudaSuccess) { parseq_destroy(e); return fail(PARSEQ_ERR_CUDA, "cudaMalloc weights"); }
+    cudaMemset(s.dev, 0, bytes);
+  }
+  int r = dev_alloc(&e->kvtab, 1ll * e->L * e->V * 2 * D);
+  if (r == PARSEQ_OK) r = dev_alloc(&e->qs, 1ll * e->L * D);
+  if (r == PARSEQ_OK) r = alloc_workspace(e);
+  if (r != PARSEQ_OK) { parseq_destroy(e); return r; }
+  *out = e;
+  return PARSEQ_OK;
+}
+
+void parseq_destroy(parseq_engine* e) {
+  if (e == nullptr) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& s : e->slots)
+    if (s.dev) cudaFree(s.dev);
+  if (e->kvtab) cudaFree(e->kvtab);
+  if (e->qs) cudaFree(e->qs);
+  free_workspace(e);
+  if (e->st_images) cudaFree(e->st_images);
+  if (e->st_logits) cudaFree(e->st_logits);
+  if (e->st_ids) cudaFree(e->st_ids);
+  if (e->st_steps) cudaFree(e->st_steps);
+  delete e;
+}
+
+int parseq_num_weights(const parseq_engine* e) { return e ? static_cast<int>(e->slots.size()) : 0; }
+const char* parseq_weight_key(const parseq_engine* e, int i, int64_t* numel) {
+  if (e == nullptr || i < 0 || i >= static_cast<int>(e->slots.size())) return nullptr;
+  if (numel) *numel = e->slots[i].numel;
+  return e->slots[i].key.c_str();
+}
+
+int parseq_set_weight(parseq_engine* e, const char* key, const float* data, int64_t numel) {
+  if (e == nullptr || key == nullptr || data == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  auto it = e->index.find(key);
+  if (it == e->index.end()) return fail(PARSEQ_ERR_INVALID_ARG, std::string("unexpected state_dict key: ") + key);
+  Slot& s = e->slots[it->second];
+  if (numel != s.numel)
+    return fail(PARSEQ_ERR_INVALID_ARG, std::string("size mismatch for ") + key + ": got " + std::to_string(numel) +
+                                            ", expected " + std::to_string(s.numel));
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  if (s.bf16) {
+    std::vector<uint16_t> tmp(static_cast<size_t>(numel));
+    for (int64_t i = 0; i < numel; ++i) tmp[static_cast<size_t>(i)] = f32_to_bf16_rne(data[i]);
+    PQ_CUDA(cudaMemcpy(s.dev, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    PQ_CUDA(cudaMemcpy(s.dev, data, static_cast<size_t>(numel) * 4, cudaMemcpyHostToDevice));
+  }
+  s.set = true;
+  e->finalized = false;
+  return PARSEQ_OK;
+}
+
+int parseq_finalize(parseq_engine* e, parseq_stream_t stream) {
+  if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
+  for (auto& s : e->slots)
+    if (!s.set) return fail(PARSEQ_ERR_STATE, "weight not set: " + s.key);
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = e->D, L = e->L, V = e->V;
+  const std::string Ly = "decoder.layers.0.";
+  const long long rows = 1ll * L * V;
+  float* ctx = nullptr;
+  __nv_bfloat16* ctxn = nullptr;
+  __nv_bfloat16* qn = nullptr;
+  PQ_TRY(dev_alloc(&ctx, rows * D));
+  PQ_TRY(dev_alloc(&ctxn, rows * D));
+  PQ_TRY(dev_alloc(&qn, 1ll * L * D));
+  pq::build_ctx_rows_kernel<<<1024, 256, 0, st>>>(e->wf("text_embed.embedding.weight"), e->wf("pos_queries"), ctx, L, V, D,
+                                                  std::sqrt(static_cast<float>(D)));
+  PQ_CUDA(cudaGetLastError());
+  int r = layernorm_launch(ctx, e->wf(Ly + "norm_c.weight"), e->wf(Ly + "norm_c.bias"), 1e-5f, static_cast<int>(rows), D,
+                           ctxn, nullptr, st);
+  // content K/V for every (position, token): rows D..3D-1 of self_attn.in_proj (enc-dec packed projection)
+  if (r == PARSEQ_OK)
+    r = gemm_launch(ctxn, D, e->wb(Ly + "self_attn.in_proj_weight") + 1ll * D * D, D,
+                    e->wf(Ly + "self_attn.in_proj_bias") + D, static_cast<int>(rows), 2 * D, D, pq::EPI_BF16, 1.0f, nullptr,
+                    0, 0, e->kvtab, 2 * D, st);
+  // query projections of the (input independent) position queries, pre-scaled by 1/sqrt(head_dim)
+  if (r == PARSEQ_OK)
+    r = layernorm_launch(e->wf("pos_queries"), e->wf(Ly + "norm_q.weight"), e->wf(Ly + "norm_q.bias"), 1e-5f, L, D, qn,
+                         nullptr, st);
+  if (r == PARSEQ_OK)
+    r = gemm_launch(qn, D, e->wb(Ly + "self_attn.in_proj_weight"), D, e->wf(Ly + "self_attn.in_proj_bias"), L, D, D,
+                    pq::EPI_F32, 1.0f / std::sqrt(static_cast<float>(e->dh_dec)), nullptr, 0, 0, e->qs, D, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(ctx);
+  cudaFree(ctxn);
+  cudaFree(qn);
+  if (r != PARSEQ_OK) return r;
+  if (ce != cudaSuccess) return fail(PARSEQ_ERR_CUDA, std::string("finalize: ") + cudaGetErrorString(ce));
+  e->finalized = true;
+  return PARSEQ_OK;
+}
+
+int parseq_forward(parseq_engine* e, const parseq_forward_args* a, const float* images, float* logits, int32_t* ids,
+                   int32_t* steps, parseq_stream_t stream) {
+  if (e == nullptr || a == nullptr || images == nullptr || logits == nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
+  if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
+  if (a->batch == 0) return PARSEQ_OK;
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int maxlen = (a->max_length < 0) ? e->cfg.max_label_length
+                                         : (a->max_length < e->cfg.max_label_length ? a->max_length : e->cfg.max_label_length);
+  const int L = maxlen + 1;
+  const bool testing = a->max_length < 0;
+  if (steps != nullptr) {
+    pq::set_int_kernel<<<1, 32, 0, st>>>(steps, (testing && a->decode_ar) ? 0 : L);
+    PQ_CUDA(cudaGetLastError());
+    e->launches++;
+  }
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  for (int b0 = 0; b0 < a->batch; b0 += e->chunk) {
+    const int B = (a->batch - b0 < e->chunk) ? (a->batch - b0) : e->chunk;
+    PQ_TRY(forward_chunk(e, a, b0, B, L, images + b0 * img_sz, logits + 1ll * b0 * L * e->C,
+                         ids ? ids + 1ll * b0 * L : nullptr, steps, st));
+  }
+  return PARSEQ_OK;
+}
+
+int parseq_forward_host(parseq_engine* e, const parseq_forward_args* a, const float* images_host, float* logits_host,
+                        int32_t* ids_host, int32_t* steps_host, parseq_stream_t stream) {
+  if (e == nullptr || a == nullptr || images_host == nullptr || logits_host == nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long B = a->batch;
+  if (B <= 0) return B == 0 ? PARSEQ_OK : fail(PARSEQ_ERR_INVALID_ARG, "negative batch");
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  if (B > e->st_batch) {
+    if (e->st_images) cudaFree(e->st_images);
+    if (e->st_logits) cudaFree(e->st_logits);
+    if (e->st_ids) cudaFree(e->st_ids);
+    if (e->st_steps) cudaFree(e->st_steps);
+    e->st_images = nullptr; e->st_logits = nullptr; e->st_ids = nullptr; e->st_steps = nullptr; e->st_batch = 0;
+    PQ_TRY(dev_alloc(&e->st_images, B * img_sz));
+    PQ_TRY(dev_alloc(&e->st_logits, B * e->L * e->C));
+    PQ_TRY(dev_alloc(&e->st_ids, B * e->L));
+    PQ_TRY(dev_alloc(&e->st_steps, 4));
+    e->st_batch = B;
+  }
+  const int maxlen = (a->max_length < 0) ? e->cfg.max_label_length
+                                         : (a->max_length < e->cfg.max_label_length ? a->max_length : e->cfg.max_label_length);
+  const long long L = maxlen + 1;
+  PQ_CUDA(cudaMemcpyAsync(e->st_images, images_host, static_cast<size_t>(B * img_sz) * 4, cudaMemcpyHostToDevice, st));
+  PQ_TRY(parseq_forward(e, a, e->st_images, e->st_logits, e->st_ids, e->st_steps, stream));
+  PQ_CUDA(cudaMemcpyAsync(logits_host, e->st_logits, static_cast<size_t>(B * L * e->C) * 4, cudaMemcpyDeviceToHost, st));
+  if (ids_host) PQ_CUDA(cudaMemcpyAsync(ids_host, e->st_ids, static_cast<size_t>(B * L) * 4, cudaMemcpyDeviceToHost, st));
+  if (steps_host) PQ_CUDA(cudaMemcpyAsync(steps_host, e->st_steps, 4, cudaMemcpyDeviceToHost, st));
+  PQ_CUDA(cudaStreamSynchronize(st));
+  return PARSEQ_OK;
+}
+
+int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* memory, parseq_stream_t stream) {
+  if (e == nullptr || images == nullptr || memory == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called");
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  for (int b0 = 0; b0 < batch; b0 += e->chunk) {
+    const int B = (batch - b0 < e->chunk) ? (batch - b0) : e->chunk;
+    PQ_TRY(encode_chunk(e, images + b0 * img_sz, B, memory + 1ll * b0 * e->T * e->D, st));
+  }
+  return PARSEQ_OK;
+}
+
+int64_t parseq_kernel_launches(const parseq_engine* e) { return e ? e->launches : 0; }
+
+int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
+  if (name == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null option");
+  const std::string n(name);
+  if (n == "block_n") {
+    if (value != 0 && value != 64 && value != 128 && value != 256) return fail(PARSEQ_ERR_INVALID_ARG, "block_n: 0/64/128/256");
+    g_block_n_override = static_cast<int>(value);
+    return PARSEQ_OK;
+  }
+  if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
+  if (n == "timing") {
+    e->timing = value != 0;
+    for (auto& t : e->timed) { e->event_pool.push_back(t.a); e->event_pool.push_back(t.b); }
+    e->timed.clear();
+    return PARSEQ_OK;
+  }
+  if (n == "chunk") {
+    if (value <= 0 || value > 4096) return fail(PARSEQ_ERR_INVALID_ARG, "chunk out of range");
+    PQ_CUDA(cudaSetDevice(e->cfg.device));
+    PQ_CUDA(cudaDeviceSynchronize());
+    free_workspace(e);
+    e->chunk = static_cast<int>(value);
+    return alloc_workspace(e);
+  }
+  return fail(PARSEQ_ERR_INVALID_ARG, "unknown option: " + n);
+}
+
+int parseq_get_timing(parseq_engine* e, int category, double* ms, double* flops, int64_t* count) {
+  if (e == nullptr || category < 0 || category >= CAT_COUNT) return fail(PARSEQ_ERR_INVALID_ARG, "bad timing query");
+  double tms = 0.0, tf = 0.0;
+  int64_t n = 0;
+  for (auto& t : e->timed) {
+    if (t.cat != category) continue;
+    float dt = 0.f;
+    cudaError_t ce = cudaEventElapsedTime(&dt, t.a, t.b);
+    if (ce != cudaSuccess) return fail(PARSEQ_ERR_CUDA, std::string("timing readback: ") + cudaGetErrorString(ce));
+    tms += dt; tf += t.flops; ++n;
+  }
+  if (ms) *ms = tms;
+  if (flops) *flops = tf;
+  if (count) *count = n;
+  return PARSEQ_OK;
+}
+
+int parseq_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int N, int K,
+                     int mode, float alpha, const float* resid, int64_t ldr, int resid_mod, void* out, int64_t ldo,
+                     parseq_stream_t stream) {
+  if (mode < 0 || mode > 2) return fail(PARSEQ_ERR_INVALID_ARG, "bad epilogue mode");
+  return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y_bf16,
+                          float* y_f32_or_null, parseq_stream_t stream) {
+  return layernorm_launch(x, gamma, beta, eps, M, D, y_bf16, y_f32_or_null, reinterpret_cast<cudaStream_t>(stream));
+}
+int parseq_enc_attention(const void* qkv_bf16, int B, int T, int D, int heads, void* out_bf16, parseq_stream_t stream) {
+  return enc_attention_launch(qkv_bf16, B, T, D, heads, out_bf16, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+// Non-GEMM kernels of the PARSeq path: patch gather (im2col), LayerNorm, ViT attention core,
+// decoder two-stream self-attention over the (position, token) K/V table, cross-attention over the
+// cached image K/V, greedy argmax / refine-context construction, early-exit step count.
+#pragma once
+#include "ptx.cuh"
+
+namespace pq {
+
+// ---------------------------------------------------------------------------------------------
+// Patch gather: images fp32 NCHW [B,3,H,W] -> A_pe bf16 [B*T, Kp] with token t = r*gw + c and
+// k = ch*ph*pw + dy*pw + dx  (Conv2d(3,D,k=s=patch) as a GEMM; timm PatchEmbed via modules.py:145-161).
+// One thread per (token, ch, dy): reads pw contiguous floats, writes pw contiguous bf16.
+__global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
+                                    int W, int ph, int pw, int gh, int gw) {
+  const long long total = static_cast<long long>(B) * gh * gw * 3 * ph;
+  const int Kp = 3 * ph * pw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // order: b, r, dy, ch, c  -> consecutive threads walk along an image row (coalesced reads)
+    long long t = i;
+    const int c = static_cast<int>(t % gw); t /= gw;
+    const int ch = static_cast<int>(t % 3); t /= 3;
+    const int dy = static_cast<int>(t % ph); t /= ph;
+    const int r = static_cast<int>(t % gh); t /= gh;
+    const int b = static_cast<int>(t);
+    const float* src = img + ((static_cast<long long>(b) * 3 + ch) * H + (r * ph + dy)) * W + c * pw;
+    __nv_bfloat16* dst = out + (static_cast<long long>(b) * gh * gw + r * gw + c) * Kp + ch * ph * pw + dy * pw;
+    for (int dx = 0; dx < pw; ++dx) dst[dx] = __float2bfloat16_rn(src[dx]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (biased variance, two-pass in registers), one warp per row.
+// y_bf16 = bf16(LN(x)); optional fp32 copy (encoder output `memory`).
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int M,
+                                                        __nv_bfloat16* __restrict__ y, float* __restrict__ y32) {
+  static_assert(D % 64 == 0, "D must be a multiple of 64");
+  constexpr int NV = D / 64;  // float2 per lane
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float2* xr = reinterpret_cast<const float2*>(x + static_cast<long long>(row) * D);
+  float2 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += v[i].x + v[i].y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean;
+    q += a * a + b * b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / D) + eps);
+  const float2* g2 = reinterpret_cast<const float2*>(gamma);
+  const float2* b2 = reinterpret_cast<const float2*>(beta);
+  uint32_t* yr = reinterpret_cast<uint32_t*>(y + static_cast<long long>(row) * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float2 g = __ldg(g2 + i * 32 + lane), b = __ldg(b2 + i * 32 + lane);
+    const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    yr[i * 32 + lane] = pack_bf16(o0, o1);
+    if (y32 != nullptr) reinterpret_cast<float2*>(y32 + static_cast<long long>(row) * D)[i * 32 + lane] = make_float2(o0, o1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ViT attention core for T = 128 tokens, head dim 64 (timm Attention: softmax(QK^T / 8) V, no mask).
+// One CTA per (image, head), 8 warps x 16 query rows.  Q/K/V tiles (128x64 bf16) are staged in
+// XOR-swizzled shared memory with cp.async; S = QK^T and O = PV run on mma.sync m16n8k16 with the
+// probabilities kept in registers (bf16 A fragments), fp32 row statistics, O/rowsum -> bf16.
+constexpr int ATT_T = 128;
+constexpr int ATT_DH = 64;
+__device__ __forceinline__ uint32_t att_swz(int r, int c) {  // element offset of (row r, col c), c%8==0 chunks
+  return static_cast<uint32_t>(r * ATT_DH + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7)));
+}
+__global__ void __launch_bounds__(256) enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out, int D, int heads) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[ATT_T * ATT_DH];
+  __shared__ __align__(128) __nv_bfloat16 sK[ATT_T * ATT_DH];
+  __shared__ __align__(128) __nv_bfloat16 sV[ATT_T * ATT_DH];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ld = 3ll * D;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * ATT_T * ld + h * ATT_DH;
+  // 3 matrices x 128 rows x 8 chunks of 16 B
+  for (int i = tid; i < 3 * ATT_T * 8; i += 256) {
+    const int m = i / (ATT_T * 8);
+    const int r = (i / 8) % ATT_T;
+    const int ck = i % 8;
+    const __nv_bfloat16* src = base + static_cast<long long>(r) * ld + m * D + ck * 8;
+    __nv_bfloat16* dstm = (m == 0) ? sQ : (m == 1) ? sK : sV;
+    cp_async_16(smem_u32(dstm + att_swz(r, ck * 8)), src);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  // ---- Q fragments for the 4 k-steps over d ----
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int col = kt * 16 + (lane >> 4) * 8;
+    ldmatrix_x4(smem_u32(sQ + att_swz(row, col)), qf[kt][0], qf[kt][1], qf[kt][2], qf[kt][3]);
+  }
+  // ---- S = Q K^T : 16 n-tiles of 8 keys ----
+  float sacc[16][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+    for (int np = 0; np < 8; ++np) {
+      const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+      const int col = kt * 16 + ((lane >> 3) & 1) * 8;
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4(smem_u32(sK + att_swz(key, col)), b0, b1, b2, b3);
+      mma_bf16_16816(sacc[2 * np], qf[kt][0], qf[kt][1], qf[kt][2], qf[kt][3], b0, b1);
+      mma_bf16_16816(sacc[2 * np + 1], qf[kt][0], qf[kt][1], qf[kt][2], qf[kt][3], b2, b3);
+    }
+  }
+  // ---- softmax over 128 keys; rows g (c0,c1) and g+8 (c2,c3) ----
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // d^-0.5 * log2(e)
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    sacc[nt][0] = exp2f((sacc[nt][0] - mx0) * kScaleLog2);
+    sacc[nt][1] = exp2f((sacc[nt][1] - mx0) * kScaleLog2);
+    sacc[nt][2] = exp2f((sacc[nt][2] - mx1) * kScaleLog2);
+    sacc[nt][3] = exp2f((sacc[nt][3] - mx1) * kScaleLog2);
+    sum0 += sacc[nt][0] + sacc[nt][1];
+    sum1 += sacc[nt][2] + sacc[nt][3];
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  // ---- O = P V : 8 k-steps over keys, 8 n-tiles over d ----
+  float oacc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint32_t a0 = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+    const uint32_t a1 = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+    const uint32_t a2 = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+    const uint32_t a3 = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int col = np * 16 + (lane >> 4) * 8;
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4_trans(smem_u32(sV + att_swz(key, col)), b0, b1, b2, b3);
+      mma_bf16_16816(oacc[2 * np], a0, a1, a2, a3, b0, b1);
+      mma_bf16_16816(oacc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+  // ---- normalise, stage through this warp's (now dead) Q rows, coalesced 16-B stores ----
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  const int g = lane >> 2, t = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * t;
+    *reinterpret_cast<uint32_t*>(sQ + att_swz(r0 + g, col)) = pack_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sQ + att_swz(r0 + g + 8, col)) = pack_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+  }
+  __syncwarp();
+  __nv_bfloat16* obase = out + static_cast<long long>(b) * ATT_T * D + h * ATT_DH;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = i * 32 + lane;       // 16 rows x 8 chunks
+    const int r = r0 + (idx >> 3), ck = idx & 7;
+    const uint4 val = *reinterpret_cast<const uint4*>(sQ + att_swz(r, ck * 8));
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * D + ck * 8) = val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder context rows for the (position, token) K/V table:
+//   ctx[pos*V + tok] = sqrt(D)*E[tok] + (pos >= 1 ? pos_queries[pos-1] : 0)     (model.py:94-99, modules.py:175-176)
+__global__ void build_ctx_rows_kernel(const float* __restrict__ emb, const float* __restrict__ posq, float* __restrict__ ctx,
+                                      int L, int V, int D, float sqrtD) {
+  const long long total = static_cast<long long>(L) * V * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D);
+    const int tok = static_cast<int>((i / D) % V);
+    const int pos = static_cast<int>(i / (static_cast<long long>(D) * V));
+    float v = sqrtD * emb[static_cast<long long>(tok) * D + c];
+    if (pos >= 1) v = posq[static_cast<long long>(pos - 1) * D + c] + v;
+    ctx[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder self-attention (query stream; DecoderLayer.forward_stream step 1, modules.py:69-72) for
+// head dim 32: one CTA per (image, query), one warp per head, lane = channel inside the head.
+//   q      : Qs[qpos] fp32 (W_q LN_q(pos_queries[qpos]) + b, pre-scaled by 1/sqrt(32); input independent)
+//   K/V    : kvtab[(k*V + ids[b,k]) * 2D + {0, D} + c] bf16   (content stream is a function of
+//            (position, token) only at decoder depth 1)
+//   mask   : mode 0 (AR step / NAR): keys 0..nkeys-1 all visible (model.py:130-136: the sliced
+//            causal row is all-False);  mode 1 (cloze refine): key k masked iff k == q+1 or an EOS
+//            occurs in ids[b, 0..k] (model.py:157,163)
+// out bf16 [B*nq, D] (A operand of the out-projection GEMM).
+__global__ void dec_self_attn_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
+                                     const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
+                                     int mode, int eos_id, __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.x / nq, qi = blockIdx.x % nq;
+  const int qpos = q0 + qi;
+  const int c = threadIdx.x;             // channel; blockDim.x == D
+  const int lane = threadIdx.x & 31;
+  __shared__ int s_ids[32];
+  __shared__ int s_first_eos;
+  if (threadIdx.x < 32) {
+    int id = (threadIdx.x < nkeys) ? ids[static_cast<long long>(b) * ids_ld + threadIdx.x] : -1;
+    s_ids[threadIdx.x] = id;
+    const unsigned m = __ballot_sync(0xffffffffu, id == eos_id);
+    if (threadIdx.x == 0) s_first_eos = (m != 0u) ? (__ffs(m) - 1) : 1 << 30;
+  }
+  __syncthreads();
+  const float q = Qs[static_cast<long long>(qpos) * D + c];
+  const int first_eos = s_first_eos;
+  float my_s = -INFINITY;                // lane k keeps the score of key k
+  for (int k = 0; k < nkeys; ++k) {
+    const __nv_bfloat16* kr = kvtab + (static_cast<long long>(k) * V + s_ids[k]) * 2 * D;
+    float part = q * __bfloat162float(kr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const bool masked = (mode == 1) && (k == qpos + 1 || k >= first_eos);
+    if (lane == k) my_s = masked ? -INFINITY : part;
+  }
+  float mx = my_s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = (lane < nkeys) ? expf(my_s - mx) : 0.f;   // exp(-inf)=0 for masked keys
+  float sum = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float pme = e / sum;
+  float acc = 0.f;
+  for (int k = 0; k < nkeys; ++k) {
+    const float pk = __shfl_sync(0xffffffffu, pme, k);
+    const __nv_bfloat16* vr = kvtab + (static_cast<long long>(k) * V + s_ids[k]) * 2 * D + D;
+    acc += pk * __bfloat162float(vr[c]);
+  }
+  out[static_cast<long long>(blockIdx.x) * D + c] = __float2bfloat16_rn(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder cross-attention (forward_stream step 2, modules.py:74-75) over the per-image K/V cache
+// kv bf16 [B, T, 2D] (K cols [0,D), V cols [D,2D)); q fp32 [B*nq, D] already scaled by 1/sqrt(32).
+// One CTA per (image, query), one warp per head: scores with lane = key (each lane dots one
+// 32-wide key row), softmax across the warp, then lane = channel for P.V.  No mask.
+template <int MAXT>
+__global__ void dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv, int T, int D,
+                                      int nq, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float s_cross[];     // [heads][32] q  +  [heads][MAXT] p
+  const int heads = blockDim.x >> 5;
+  float* s_q = s_cross;
+  float* s_p = s_cross + heads * 32;
+  const int b = blockIdx.x / nq;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = threadIdx.x;
+  s_q[c] = q[static_cast<long long>(blockIdx.x) * D + c];
+  __syncwarp();
+  const __nv_bfloat16* kvb = kv + static_cast<long long>(b) * T * 2 * D;
+  constexpr int R = MAXT / 32;
+  float sc[R];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = r * 32 + lane;
+    float s = -INFINITY;
+    if (t < T) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + h * 32);
+      s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = __ldg(kr + j);
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(p2[e]);
+          s += s_q[h * 32 + j * 8 + e * 2] * f.x;
+          s += s_q[h * 32 + j * 8 + e * 2 + 1] * f.y;
+        }
+      }
+    }
+    sc[r] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = r * 32 + lane;
+    const float e = (t < T) ? expf(sc[r] - mx) : 0.f;
+    sc[r] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = r * 32 + lane;
+    if (t < T) s_p[h * MAXT + t] = sc[r] * inv;
+  }
+  __syncwarp();
+  float acc = 0.f;
+  const __nv_bfloat16* vb = kvb + D + c;
+  for (int t = 0; t < T; ++t) acc += s_p[h * MAXT + t] * __bfloat162float(vb[static_cast<long long>(t) * 2 * D]);
+  out[static_cast<long long>(blockIdx.x) * D + c] = __float2bfloat16_rn(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Greedy argmax (first maximum wins, torch.argmax semantics) of logits rows -> token ids.
+// One warp per row.  Row r = (b, s): reads logits[b, src_pos0 + s, :C], writes ids[b*ids_ld + dst_pos0 + s].
+// If `forced` != nullptr the written id is forced[b*forced_ld + dst_pos0 + s] (teacher forcing).
+__global__ void argmax_rows_kernel(const float* __restrict__ logits, int L, int C, int B, int nrows_per_b, int src_pos0,
+                                   int* __restrict__ ids, int ids_ld, int dst_pos0, const int* __restrict__ forced,
+                                   int forced_ld) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= B * nrows_per_b) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / nrows_per_b, s = w % nrows_per_b;
+  const float* row = logits + (static_cast<long long>(b) * L + src_pos0 + s) * C;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < C; j += 32) {
+    const float v = row[j];
+    if (v > best) { best = v; bi = j; }    // strictly greater: keeps the lowest index within the lane
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    int v = bi;
+    if (forced != nullptr) v = forced[static_cast<long long>(b) * forced_ld + dst_pos0 + s];
+    ids[static_cast<long long>(b) * ids_ld + dst_pos0 + s] = v;
+  }
+}
+
+__global__ void fill_ids_kernel(int* __restrict__ ids, int B, int ld, int bos, int pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * ld) ids[i] = ((i % ld) == 0) ? bos : pad;
+}
+__global__ void copy_ids_kernel(const int* __restrict__ src, int src_ld, int* __restrict__ dst, int dst_ld, int B, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * n) dst[static_cast<long long>(i / n) * dst_ld + (i % n)] = src[static_cast<long long>(i / n) * src_ld + (i % n)];
+}
+
+// S = number of AR steps the reference returns under its batch-wide early exit (model.py:144):
+// smallest j>=1 such that every row has an EOS among ids[b,1..j]  == max_b first_eos_pos(b); L if any row has none.
+__global__ void ar_steps_kernel(const int* __restrict__ ids, int ids_ld, int B, int L, int eos_id, int* __restrict__ steps) {
+  int worst = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int first = L;
+    for (int j = 1; j < L; ++j)
+      if (ids[static_cast<long long>(b) * ids_ld + j] == eos_id) { first = j; break; }
+    worst = max(worst, first);
+  }
+  atomicMax(steps, worst);
+}
+__global__ void set_int_kernel(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+
+}  // namespace pq

@@ -1,0 +1,241 @@
+"""Drop-in Python surface of the PARSeq inference path.
+
+`PARSeq` mirrors `strhub.models.parseq.system.PARSeq` (system.py:33-88: ctor kwargs, `.model`,
+`.tokenizer`, `.hparams`, `forward(images, max_length)`) and the bits of `BaseSystem` its callers use
+(`test_step` -> `BatchResult`, base.py:36-44,112-143,179-180; `.device`).  `ParseqModel` mirrors the
+inner `strhub.models.parseq.model.PARSeq` (model.py:31-169): same parameter names (so released
+`parseq-*.pt` state_dicts load), `encode`, `forward(tokenizer, images, max_length)`, `decode_ar`,
+`refine_iters`, `max_label_length`.  All arithmetic happens in libparseq_b200.so (sm_100a CUDA);
+these classes only own the parameters and marshal pointers.  There is no CPU or eager-PyTorch
+fallback: calling forward with non-CUDA tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Any, Dict, Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from .config import ParseqConfig, make_config
+from .engine import Engine, EngineError
+from .tokenizer import CharsetAdapter, Tokenizer
+
+
+class InvalidModelError(RuntimeError):
+    """Raised for any model-related error (creation, loading) — name kept from strhub/models/utils.py:10."""
+
+
+@dataclass
+class BatchResult:          # base.py:36-44
+    num_samples: int
+    correct: int
+    ned: float
+    confidence: float
+    label_length: int
+    loss: Optional[Tensor]
+    loss_numel: Optional[int]
+
+
+def edit_distance(a: str, b: str) -> int:
+    """Levenshtein distance (the reference uses nltk.edit_distance, base.py:29,139)."""
+    if a == b:
+        return 0
+    if not a or not b:
+        return len(a) + len(b)
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+class _Holder(nn.Module):
+    """Parameter container; nested so that state_dict keys equal the reference's."""
+
+
+def _register(root: nn.Module, key: str, tensor: Tensor):
+    parts = key.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Holder())
+        mod = getattr(mod, p)
+    mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class ParseqModel(nn.Module):
+    def __init__(self, cfg: ParseqConfig):
+        super().__init__()
+        from .weights import init_state_dict
+        self.cfg = cfg
+        self.max_label_length = cfg.max_label_length
+        self.decode_ar = cfg.decode_ar
+        self.refine_iters = cfg.refine_iters
+        # random init with the reference's distributions (weights.py); bf16-exact not forced here
+        for k, v in init_state_dict(cfg, seed=0, perturb=False, bf16_exact=False).items():
+            _register(self, k, v)
+        self._engine: Optional[Engine] = None
+        self._engine_sig = None
+        self._chunk = 0
+
+    # ---- engine plumbing -------------------------------------------------------------------
+    @property
+    def _device(self) -> torch.device:
+        return self.pos_queries.device
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self) -> Engine:
+        dev = self._device
+        if dev.type != "cuda":
+            raise RuntimeError("parseq_b200 runs on a CUDA (sm_100a) device only; move the model with .to('cuda') "
+                               "— there is no CPU fallback")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._engine is None or self._engine.device != idx:
+            self._engine = Engine(self.cfg, idx, self._chunk)
+            self._engine_sig = None
+        sig = self._signature()
+        if sig != self._engine_sig:
+            self._engine.load_state_dict(self.state_dict(), torch.cuda.current_stream(idx).cuda_stream)
+            self._engine_sig = sig
+        return self._engine
+
+    def set_chunk(self, chunk: int):
+        self._chunk = int(chunk)
+        if self._engine is not None:
+            self._engine.set_option("chunk", chunk)
+
+    def _check_images(self, images: Tensor) -> Tensor:
+        if images.device.type != "cuda":
+            raise RuntimeError("images must be CUDA tensors (no CPU fallback)")
+        H, W = self.cfg.img_size
+        if images.dim() != 4 or images.shape[1] != 3 or tuple(images.shape[-2:]) != (H, W):
+            raise AssertionError(f"Input image size {tuple(images.shape)} doesn't match model (N,3,{H},{W})")
+        return images.to(torch.float32).contiguous()
+
+    # ---- reference API ---------------------------------------------------------------------
+    def encode(self, img: Tensor) -> Tensor:
+        eng = self.engine()
+        img = self._check_images(img)
+        mem = torch.empty((img.shape[0], self.cfg.num_patches, self.cfg.embed_dim), dtype=torch.float32,
+                          device=img.device)
+        eng.encode(img.data_ptr(), img.shape[0], mem.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream)
+        return mem
+
+    def decode(self, *args, **kwargs):
+        raise NotImplementedError("arbitrary-mask decode() is a training-time API (system.py:169-200) and is not "
+                                  "part of the inference engine")
+
+    def forward(self, tokenizer: Tokenizer, images: Tensor, max_length: Optional[int] = None,
+                return_ids: bool = False, forced_ids: Optional[Tensor] = None,
+                forced_refine: Optional[Tensor] = None):
+        eng = self.engine()
+        images = self._check_images(images)
+        dev = images.device
+        N = images.shape[0]
+        L = eng.num_steps(max_length)
+        C = self.cfg.num_classes
+        logits = torch.empty((N, L, C), dtype=torch.float32, device=dev)
+        ids = torch.empty((N, L), dtype=torch.int32, device=dev)
+        steps = torch.empty((1,), dtype=torch.int32, device=dev)
+        fi = forced_ids.to(device=dev, dtype=torch.int32).contiguous() if forced_ids is not None else None
+        fr = forced_refine.to(device=dev, dtype=torch.int32).contiguous() if forced_refine is not None else None
+        eng.forward(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream, max_length, self.decode_ar, self.refine_iters,
+                    fi.data_ptr() if fi is not None else None, fr.data_ptr() if fr is not None else None)
+        if max_length is None and self.decode_ar and not self.refine_iters:
+            # model.py:144-147: with no refinement the reference returns only the S steps it ran
+            S = int(steps.item())
+            logits, ids = logits[:, :S], ids[:, :S]
+        if return_ids:
+            return logits, ids
+        return logits
+
+
+class _HParams(SimpleNamespace):
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def __contains__(self, k):
+        return hasattr(self, k)
+
+    def keys(self):
+        return self.__dict__.keys()
+
+
+class PARSeq(nn.Module):
+    def __init__(self, charset_train: str, charset_test: str, max_label_length: int, batch_size: int = 384,
+                 lr: float = 7e-4, warmup_pct: float = 0.075, weight_decay: float = 0.0,
+                 img_size: Sequence[int] = (32, 128), patch_size: Sequence[int] = (4, 8), embed_dim: int = 384,
+                 enc_num_heads: int = 6, enc_mlp_ratio: int = 4, enc_depth: int = 12, dec_num_heads: int = 12,
+                 dec_mlp_ratio: int = 4, dec_depth: int = 1, perm_num: int = 6, perm_forward: bool = True,
+                 perm_mirrored: bool = True, decode_ar: bool = True, refine_iters: int = 1, dropout: float = 0.1,
+                 **kwargs: Any) -> None:
+        super().__init__()
+        hp = dict(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
+                  batch_size=batch_size, lr=lr, warmup_pct=warmup_pct, weight_decay=weight_decay,
+                  img_size=list(img_size), patch_size=list(patch_size), embed_dim=embed_dim,
+                  enc_num_heads=enc_num_heads, enc_mlp_ratio=enc_mlp_ratio, enc_depth=enc_depth,
+                  dec_num_heads=dec_num_heads, dec_mlp_ratio=dec_mlp_ratio, dec_depth=dec_depth, perm_num=perm_num,
+                  perm_forward=perm_forward, perm_mirrored=perm_mirrored, decode_ar=decode_ar,
+                  refine_iters=refine_iters, dropout=dropout)
+        hp.update(kwargs)
+        self.hparams = _HParams(**hp)
+        self.tokenizer = Tokenizer(charset_train)
+        self.charset_adapter = CharsetAdapter(charset_test)
+        self.bos_id, self.eos_id, self.pad_id = self.tokenizer.bos_id, self.tokenizer.eos_id, self.tokenizer.pad_id
+        self.batch_size, self.lr, self.warmup_pct, self.weight_decay = batch_size, lr, warmup_pct, weight_decay
+        cfg = ParseqConfig(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
+                           img_size=tuple(img_size), patch_size=tuple(patch_size), embed_dim=embed_dim,
+                           enc_num_heads=enc_num_heads, enc_mlp_ratio=enc_mlp_ratio, enc_depth=enc_depth,
+                           dec_num_heads=dec_num_heads, dec_mlp_ratio=dec_mlp_ratio, dec_depth=dec_depth,
+                           decode_ar=decode_ar, refine_iters=refine_iters, dropout=dropout,
+                           name=str(kwargs.get("name", "parseq")))
+        try:
+            self.model = ParseqModel(cfg)
+        except EngineError as e:  # pragma: no cover
+            raise InvalidModelError(str(e)) from e
+
+    @property
+    def device(self) -> torch.device:
+        return self.model._device
+
+    def forward(self, images: Tensor, max_length: Optional[int] = None) -> Tensor:
+        return self.model.forward(self.tokenizer, images, max_length)
+
+    # base.py:112-143,179-180 (test path only; validation loss is a training concern)
+    def _eval_step(self, batch, validation: bool = False):
+        images, labels = batch
+        logits = self.forward(images)
+        probs = logits.softmax(-1)
+        preds, probs = self.tokenizer.decode(probs)
+        correct = total = label_length = 0
+        ned = confidence = 0.0
+        for pred, prob, gt in zip(preds, probs, labels):
+            confidence += prob.prod().item()
+            pred = self.charset_adapter(pred)
+            ned += edit_distance(pred, gt) / max(len(pred), len(gt), 1)
+            correct += int(pred == gt)
+            total += 1
+            label_length += len(pred)
+        return dict(output=BatchResult(total, correct, ned, confidence, label_length, None, None))
+
+    def test_step(self, batch, batch_idx):
+        return self._eval_step(batch, False)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path: str, map_location="cpu", **kwargs):
+        """Lightning .ckpt layout: {'hyper_parameters': ctor kwargs, 'state_dict': {'model.<key>': tensor}}."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(kwargs)
+        model = cls(**hp)
+        sd = {k[len("model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("model.")}
+        model.model.load_state_dict(sd)
+        return model

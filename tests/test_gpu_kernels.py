@@ -1,0 +1,150 @@
+"""Building-block parity on the GPU: every kernel called through the C ABI (include/parseq_b200.h)
+and compared with a plain fp32 PyTorch evaluation of the same op on the same bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _gemm(lib, A, W, bias, mode, alpha=1.0, resid=None, resid_mod=0, out=None, ldo=None):
+    from parseq_b200.engine import check
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32 if mode == 0 else torch.bfloat16, device=A.device)
+    ldo = out.stride(0) if ldo is None else ldo
+    check(lib, lib.parseq_gemm_bf16(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0),
+                                    bias.data_ptr() if bias is not None else None, M, N, K, mode, alpha,
+                                    resid.data_ptr() if resid is not None else None,
+                                    resid.stride(0) if resid is not None else 0, resid_mod, out.data_ptr(), ldo,
+                                    _stream()))
+    torch.cuda.synchronize()
+    return out
+
+
+SHAPES = [
+    # M, N, K
+    (128, 128, 64), (128, 128, 384), (256, 384, 384), (1024, 1152, 384), (512, 1536, 384), (384, 384, 1536),
+    (1, 384, 384), (26, 384, 384), (52, 1536, 384), (300, 95, 384), (2522, 768, 384), (640, 384, 96),
+    (130, 576, 192), (129, 192, 768), (20000, 384, 384), (4096, 768, 384),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_f32_bias(lib, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    ref = A.float() @ W.float().t() + bias
+    out = _gemm(lib, A, W, bias, 0)
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_gemm_block_n_variants(lib, block_n):
+    from parseq_b200.engine import check
+    check(lib, lib.parseq_set_option(None, b"block_n", block_n))
+    try:
+        g = torch.Generator(device="cuda").manual_seed(block_n)
+        M, N, K = 700, 1536, 384
+        A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+        W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+        bias = torch.randn((N,), device="cuda", generator=g)
+        ref = A.float() @ W.float().t() + bias
+        out = _gemm(lib, A, W, bias, 0)
+        assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    finally:
+        check(lib, lib.parseq_set_option(None, b"block_n", 0))
+
+
+def test_gemm_residual_inplace_and_broadcast(lib):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 640, 384, 384
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    x = torch.randn((M, N), device="cuda", generator=g)
+    ref = x + (A.float() @ W.float().t() + bias)
+    out = _gemm(lib, A, W, bias, 0, resid=x, out=x)            # in place (x += ...)
+    assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    table = torch.randn((128, N), device="cuda", generator=g)  # residual row = row % 128 (pos_embed pattern)
+    ref2 = (A.float() @ W.float().t() + bias) * 0.25 + table.repeat(M // 128, 1)
+    out2 = _gemm(lib, A, W, bias, 0, alpha=0.25, resid=table, resid_mod=128)
+    assert (out2 - ref2).abs().max().item() <= 2e-4 * ref2.abs().max().item()
+
+
+def test_gemm_bf16_and_gelu(lib):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, N, K = 384, 1536, 384
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    acc = A.float() @ W.float().t() + bias
+    out = _gemm(lib, A, W, bias, 1).float()
+    assert (out - acc).abs().max().item() <= 2 ** -7 * acc.abs().max().item()      # one bf16 ulp
+    assert (out == acc.bfloat16().float()).float().mean().item() > 0.995            # rounding flips only
+    ref = torch.nn.functional.gelu(acc)
+    out = _gemm(lib, A, W, bias, 2).float()
+    assert (out - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    assert (out == ref.bfloat16().float()).float().mean().item() > 0.99
+
+
+def test_gemm_head_layout(lib):
+    """N=95 (odd row pitch -> scalar store path), strided rows (one AR step of [B, L, C] logits)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, L, C, K = 37, 26, 95, 384
+    A = torch.randn((B, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((C, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((C,), device="cuda", generator=g)
+    logits = torch.zeros((B, L, C), device="cuda")
+    step = 7
+    _gemm(lib, A, W, bias, 0, out=logits[:, step], ldo=L * C)
+    ref = A.float() @ W.float().t() + bias
+    assert (logits[:, step] - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    logits[:, step] = 0
+    assert logits.abs().max().item() == 0.0       # nothing written outside the step's rows
+
+
+@pytest.mark.parametrize("D,eps", [(192, 1e-6), (384, 1e-6), (384, 1e-5), (768, 1e-5)])
+def test_layernorm(lib, D, eps):
+    from parseq_b200.engine import check
+    g = torch.Generator(device="cuda").manual_seed(D)
+    M = 1000
+    x = torch.randn((M, D), device="cuda", generator=g) * 3 + 0.5
+    gamma = torch.randn((D,), device="cuda", generator=g)
+    beta = torch.randn((D,), device="cuda", generator=g)
+    y = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+    y32 = torch.empty((M, D), dtype=torch.float32, device="cuda")
+    check(lib, lib.parseq_layernorm_bf16(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, D, y.data_ptr(),
+                                         y32.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps)
+    assert (y32 - ref).abs().max().item() <= 2e-5
+    assert (y.float() == y32.bfloat16().float()).all()
+
+
+@pytest.mark.parametrize("B,heads", [(1, 6), (5, 6), (3, 3), (2, 12)])
+def test_enc_attention(lib, B, heads):
+    from parseq_b200.engine import check
+    T, d = 128, 64
+    D = heads * d
+    g = torch.Generator(device="cuda").manual_seed(B * 10 + heads)
+    qkv = (torch.randn((B * T, 3 * D), device="cuda", generator=g) * 1.5).bfloat16()
+    out = torch.empty((B * T, D), dtype=torch.bfloat16, device="cuda")
+    check(lib, lib.parseq_enc_attention(qkv.data_ptr(), B, T, D, heads, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().reshape(B, T, 3, heads, d).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * (d ** -0.5)
+    e = torch.exp(s - s.max(-1, keepdim=True).values)
+    o = (e.bfloat16().float() @ v) / e.sum(-1, keepdim=True)
+    ref = o.permute(0, 2, 1, 3).reshape(B * T, D)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err

@@ -1,0 +1,227 @@
+"""End-to-end parity of the CUDA engine (strhub-compatible module -> C ABI -> sm_100a kernels) with
+  (a) the committed golden outputs of the reference's own modules (tests/golden, fp32), and
+  (b) the CPU oracle recomputed here on the same seeded inputs.
+
+Numerics contract (DESIGN.md "Numerics"): the engine feeds bf16 operands to the tensor cores with fp32
+accumulation, fp32 residual stream / LayerNorm / softmax statistics / logits.  bf16 operand rounding makes
+every bf16 implementation (the precision-matched oracle included) deviate from the fp32 reference by
+~1e-3 mean / <2e-2 max on the logits (sigma(logit) ~ 0.4 with the synthetic weights), and because rounding
+decisions cascade through 12 blocks, two bf16 implementations agree with each other no better than with
+fp32 at full depth.  Hence:
+  * TOL_FP32_MAX / TOL_FP32_MEAN : engine logits vs the fp32 reference under teacher forcing (every row).
+  * TAU                          : argmax decisions whose fp32 top1-top2 margin exceeds TAU must be
+                                   bit-identical (every such decision, every row).
+  * free-running decoded ids must be bit-identical to the reference on the margin-filtered sets
+    (tests/golden/filtered_*.pt: every argmax margin of the fp32 run > tau=0.02).
+  * rounding points are pinned at shallow depth, where the matched oracle IS tight (test_rounding_points...).
+"""
+import glob
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_FP32_MAX = 2.0e-2
+TOL_FP32_MEAN = 3.0e-3
+TAU = 2.0e-2
+
+
+def _model(experiment, seed, eos_bias=0.0, **kw):
+    from parseq_b200.config import make_config
+    from parseq_b200.factory import create_model
+    from parseq_b200.weights import init_state_dict
+    cfg = make_config(experiment, **{k: v for k, v in kw.items() if k in ("enc_depth",)})
+    sd = init_state_dict(cfg, seed)
+    if eos_bias:
+        sd["head.bias"] = sd["head.bias"].clone()
+        sd["head.bias"][0] += eos_bias
+    m = create_model(experiment, **kw)
+    m.model.load_state_dict(sd)
+    return cfg, sd, m.eval().to("cuda")
+
+
+def _decisions_ok(engine_logits, ref_logits, tau):
+    """Every argmax decision whose reference margin exceeds tau is bit-identical."""
+    top2 = ref_logits.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > tau
+    same = engine_logits.argmax(-1) == ref_logits.argmax(-1)
+    return bool(same[clear].all()), int(clear.sum()), int(clear.numel())
+
+
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if not os.path.basename(p).startswith("filtered"))
+
+
+@pytest.mark.parametrize("path", CASES, ids=lambda p: os.path.basename(p)[:-3])
+def test_teacher_forced_vs_reference_golden(path):
+    """All decode modes of model.py:105-169 (AR / NAR / cloze refine x1..3 / max_length / EOS early exit),
+    forcing the reference run's own id trajectory so that near-ties cannot fork the comparison."""
+    from parseq_b200.weights import synth_images, state_dict_digest
+    blob = torch.load(path, weights_only=False)
+    cfg, sd, m = _model(blob["experiment"], blob["weight_seed"], blob["eos_bias"], decode_ar=blob["decode_ar"],
+                        refine_iters=blob["refine_iters"])
+    assert state_dict_digest(sd) == blob["sd_digest"]
+    x = synth_images(cfg, blob["batch"], blob["image_seed"])
+    ref = blob["logits"]
+    L = m.model.engine().num_steps(blob["max_length"])
+    forced = forced_refine = None
+    if blob["ar_ids"] is not None:
+        forced = torch.full((blob["batch"], L), 96, dtype=torch.int32)
+        forced[:, : blob["ar_ids"].shape[1]] = blob["ar_ids"]
+    if blob["refine_ctx"]:
+        forced_refine = torch.full((len(blob["refine_ctx"]), blob["batch"], L), 96, dtype=torch.int32)
+        for r, c in enumerate(blob["refine_ctx"]):
+            forced_refine[r, :, : c.shape[1]] = c
+            # positions beyond the reference's early-exit length S are masked anyway (>= first EOS); fill with EOS
+            forced_refine[r, :, c.shape[1]:] = 0
+    with torch.inference_mode():
+        logits = m.model.forward(m.tokenizer, x.cuda(), blob["max_length"], forced_ids=forced,
+                                 forced_refine=forced_refine).cpu()
+    if blob["decode_ar"] and not blob["refine_iters"] and blob["max_length"] is None:
+        # early-exit length S (model.py:144-147) comes from the engine's own free-running ids only when nothing
+        # is forced; under forcing it must equal the reference's S
+        assert logits.shape[1] == blob["steps"] == ref.shape[1]
+    assert logits.shape == ref.shape
+    err = (logits - ref).abs()
+    assert err.max().item() <= TOL_FP32_MAX, err.max().item()
+    assert err.mean().item() <= TOL_FP32_MEAN, err.mean().item()
+    ok, n_clear, n_all = _decisions_ok(logits, ref, TAU)
+    assert ok, f"argmax mismatch on a decision with margin > {TAU} ({n_clear}/{n_all} clear decisions)"
+
+
+@pytest.mark.parametrize("name", ["filtered_s_ar1", "filtered_s_ar1_len5", "filtered_ti_ar1_len5"])
+def test_free_running_ids_bit_identical_on_margin_filtered_set(name):
+    """Free-running (no forcing) greedy decode: token-id sequences bit-identical to the fp32 reference on
+    every image of the margin-filtered set."""
+    from parseq_b200.weights import synth_images, state_dict_digest
+    path = os.path.join(GOLDEN, name + ".pt")
+    blob = torch.load(path, weights_only=False)
+    tol = TOL_FP32_MAX
+    cfg, sd, m = _model(blob["experiment"], blob["weight_seed"], decode_ar=blob["decode_ar"],
+                        refine_iters=blob["refine_iters"])
+    assert state_dict_digest(sd) == blob["sd_digest"]
+    assert len(blob["picks"]) >= 4
+    cache = {}
+    imgs = []
+    for seed, k in blob["picks"]:
+        if seed not in cache:
+            cache[seed] = synth_images(cfg, blob["block"], seed)
+        imgs.append(cache[seed][k])
+    x = torch.stack(imgs)
+    with torch.inference_mode():
+        logits, ids = m.model.forward(m.tokenizer, x.cuda(), blob["max_length"], return_ids=True)
+    logits, ids = logits.cpu(), ids.cpu()
+    assert torch.equal(ids, blob["ids"]), "decoded ids differ from the reference on the margin-filtered set"
+    assert (logits - blob["logits"]).abs().max().item() <= TOL_FP32_MAX
+
+
+@pytest.mark.parametrize("experiment,B,ar,ri,ml", [("parseq", 64, True, 1, None), ("parseq", 48, False, 2, None),
+                                                    ("parseq-tiny", 64, True, 1, None), ("parseq", 40, True, 0, 9)])
+def test_decisions_vs_live_fp32_oracle(experiment, B, ar, ri, ml):
+    """Fresh seeds, oracle recomputed on this host: teacher-forced logits within tolerance on every row and
+    every clear decision identical; free-running per-decision agreement reported and loosely bounded."""
+    from oracle.parseq_oracle import ParseqOracle
+    from parseq_b200.weights import synth_images
+    cfg, sd, m = _model(experiment, 3, decode_ar=ar, refine_iters=ri)
+    x = synth_images(cfg, B, 42)
+    o = ParseqOracle(cfg, sd, "fp32").forward(x, ml, ar, ri)
+    forced = o.ar_ids.int() if o.ar_ids is not None else None
+    forced_refine = torch.stack([c.int() for c in o.refine_ctx]) if o.refine_ctx else None
+    with torch.inference_mode():
+        lf = m.model.forward(m.tokenizer, x.cuda(), ml, forced_ids=forced, forced_refine=forced_refine).cpu()
+        lfree, ids_free = m.model.forward(m.tokenizer, x.cuda(), ml, return_ids=True)
+    err = (lf - o.logits).abs()
+    assert err.max().item() <= TOL_FP32_MAX and err.mean().item() <= TOL_FP32_MEAN, (err.max().item(), err.mean().item())
+    ok, n_clear, n_all = _decisions_ok(lf, o.logits, TAU)
+    assert ok and n_clear > n_all // 4
+    agree = (ids_free.cpu().long() == o.ids).float().mean().item()
+    assert agree >= 0.85, agree          # near-tie forks only; see module docstring
+
+
+def test_rounding_points_pinned_at_depth1():
+    """At encoder depth 1 the cascade has not started: the engine must sit an order of magnitude closer to the
+    precision-matched (bf16-operand) oracle than to fp32 — i.e. it rounds where DESIGN.md says it rounds."""
+    from oracle.parseq_oracle import ParseqOracle
+    from parseq_b200.weights import synth_images
+    cfg, sd, m = _model("parseq", 0, enc_depth=1)
+    x = synth_images(cfg, 4, 5)
+    with torch.inference_mode():
+        mem = m.model.encode(x.cuda()).cpu()
+    ob = ParseqOracle(cfg, sd, "bf16").encode(x)
+    o32 = ParseqOracle(cfg, sd, "fp32").encode(x)
+    e_matched = (mem - ob).abs().mean().item()
+    e_fp32 = (mem - o32).abs().mean().item()
+    assert e_matched <= 2.5e-4, e_matched
+    assert e_matched * 5 <= e_fp32, (e_matched, e_fp32)
+
+
+def test_encode_vs_reference_memory():
+    from parseq_b200.weights import synth_images
+    cfg, sd, m = _model("parseq", 0)
+    blob = torch.load(os.path.join(GOLDEN, "s_ar1_b2.pt"), weights_only=False)
+    x0 = synth_images(cfg, 2, 0)
+    with torch.inference_mode():
+        mem0 = m.model.encode(x0.cuda()).cpu()[0]
+    err = (mem0 - blob["memory0"]).abs()
+    assert err.max().item() <= 5e-2 and err.mean().item() <= 5e-3, (err.max().item(), err.mean().item())
+
+
+def test_early_exit_length_free_running():
+    """`max_length=None`, AR, no refine: returned length S follows the reference's batch-wide EOS early exit."""
+    from parseq_b200.weights import synth_images
+    blob = torch.load(os.path.join(GOLDEN, "s_eos_ar0_b4.pt"), weights_only=False)
+    cfg, sd, m = _model("parseq", blob["weight_seed"], blob["eos_bias"], decode_ar=True, refine_iters=0)
+    x = synth_images(cfg, blob["batch"], blob["image_seed"])
+    with torch.inference_mode():
+        logits = m.model.forward(m.tokenizer, x.cuda(), None).cpu()
+    if bool((blob["min_margin_fp64"] > 1e-2).all()):
+        assert logits.shape == blob["logits"].shape
+    assert 1 <= logits.shape[1] <= 26
+    S = logits.shape[1]
+    ids = logits.argmax(-1)
+    has_eos = (ids == 0).any(dim=1)
+    assert S == 26 or bool(has_eos.all())
+
+
+def test_full_size_properties_bs512():
+    """BASELINE configs[1] size (bs=512, AR + 1 refine): size-independent properties —
+    (i) batch-composition invariance: rows computed inside a 512 batch (4 internal chunks) are bit-identical to
+        the same images run in another order / alone; (ii) determinism; (iii) ids == argmax(logits)."""
+    from parseq_b200.weights import synth_images
+    cfg, sd, m = _model("parseq", 0)
+    x = synth_images(cfg, 512, 77).cuda()
+    with torch.inference_mode():
+        l1, i1 = m.model.forward(m.tokenizer, x, None, return_ids=True)
+        l2, i2 = m.model.forward(m.tokenizer, x, None, return_ids=True)
+        perm = torch.randperm(512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+        l3, _ = m.model.forward(m.tokenizer, x[perm], None, return_ids=True)
+        l4, _ = m.model.forward(m.tokenizer, x[:7], None, return_ids=True)
+    assert l1.shape == (512, 26, 95)
+    assert torch.equal(l1, l2) and torch.equal(i1, i2)
+    assert torch.equal(l1[perm], l3)
+    assert torch.equal(l1[:7], l4)
+    assert torch.equal(i1.long(), l1.argmax(-1))
+    assert torch.isfinite(l1).all()
+
+
+def test_module_api_contract():
+    """Surface used by the reference's callers (bench.py:39-46, read.py:37-47, test.py:92-121)."""
+    import hubconf
+    from parseq_b200.weights import synth_images
+    m = hubconf.parseq(pretrained=False, refine_iters=1).eval().to("cuda")
+    x = synth_images(m.model.cfg, 3, 1).cuda()
+    with torch.inference_mode():
+        logits = m(x)
+        assert logits.shape == (3, 26, 95) and logits.dtype == torch.float32      # README.md:111-112
+        assert m(x, 7).shape == (3, 8, 95)
+        labels, probs = m.tokenizer.decode(logits.softmax(-1))
+        assert len(labels) == 3 and all(isinstance(s, str) for s in labels)
+        res = m.test_step((x, ["abc", "de", "f"]), -1)["output"]
+        assert res.num_samples == 3
+    assert m.hparams.img_size == [32, 128] and m.device.type == "cuda"
+    with pytest.raises(RuntimeError):
+        m(x.cpu())
+    with pytest.raises(AssertionError):
+        m(x[:, :, :16])
