@@ -33,7 +33,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
-    ap.add_argument("--chunk", type=int, default=0, help="engine-internal chunk (0 = default)")
+    ap.add_argument("--chunk", type=int, default=0, help="images per pipeline stage (0 = engine default)")
+    ap.add_argument("--max-batch", type=int, default=0, help="images per super-chunk / CUDA graph (0 = default)")
+    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     return ap.parse_args()
@@ -99,14 +101,33 @@ class ClockSampler:
         return out
 
 
+def pick_cpu_threads(o, cfg):
+    """torch's intra-op pool is not automatically fastest at os.cpu_count() threads on a many-core host (the
+    decoder's small matmuls oversubscribe); give the CPU arm its best thread count from a short probe."""
+    import torch
+    from parseq_b200.weights import synth_images
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    probe = synth_images(cfg, 16, 7)
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        o.forward(probe[:4], None, True, 1)
+        t0 = time.perf_counter(); o.forward(probe, None, True, 1); dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def oracle_images_per_sec(cfg, sd, batch, repeats, decode_ar=True, refine_iters=1):
     """Reference-style CPU path: fp32 restatement of model.py:105-169 (oracle, pinned to the reference's
-    own modules by tests/golden) on all host threads."""
+    own modules by tests/golden) on the host cores (best thread count of a short probe)."""
     import torch
     from oracle.parseq_oracle import ParseqOracle
     from parseq_b200.weights import synth_images
-    torch.set_num_threads(os.cpu_count() or 1)
     o = ParseqOracle(cfg, sd, "fp32")
+    pick_cpu_threads(o, cfg)
     x = synth_images(cfg, batch, 4242)
     o.forward(x[: max(1, batch // 8)], None, decode_ar, refine_iters)     # warm-up
     ts = []
@@ -127,10 +148,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
     cfg = make_config("parseq")
     sd = init_state_dict(cfg, 0)
     o = ParseqOracle(cfg, sd, "fp32")
+    pick_cpu_threads(o, cfg)
     probe = synth_images(cfg, 8, 1)
     o.forward(probe, None, True, 1)
     t0 = time.perf_counter(); o.forward(probe, None, True, 1); dt = time.perf_counter() - t0
@@ -186,8 +207,12 @@ def main():
     sd = init_state_dict(cfg, 0)
     model = create_model("parseq", decode_ar=True, refine_iters=1)
     model.model.load_state_dict(sd)
+    if args.max_batch:
+        model.model.set_engine_option("max_batch", args.max_batch)
     if args.chunk:
-        model.model.set_chunk(args.chunk)
+        model.model.set_engine_option("chunk", args.chunk)
+    if args.no_graph:
+        model.model.set_engine_option("use_graph", 0)
     model = model.eval().to(dev)
     eng = model.model.engine()
     B = args.batch
@@ -320,7 +345,7 @@ def main():
         "config": {"workload": "PARSeq-S 32x128 94-char max_len=25 bs=512/GPU AR + 1 refine (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, no collective)",
                    "l2": f"inputs rotate over {NROT} resident batches ({NROT * B * 49152 / 1e6:.0f} MB > 126 MB L2)",
-                   "chunk": eng.cfg and (args.chunk or 128)},
+                   "chunk": args.chunk or 128, "max_batch": args.max_batch or 512, "cuda_graph": not args.no_graph},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1000 * e2e_s / args.steps},

@@ -43,7 +43,7 @@ typedef struct parseq_config {
   int32_t dec_num_heads, dec_mlp_ratio, dec_depth;   /* dec_depth must be 1 (all reference configs) */
   int32_t max_label_length;              /* 25 -> 26 decode positions */
   int32_t num_tokens;                    /* 97: EOS=0, chars 1..94, BOS=95, PAD=96 (data/utils.py:102-111) */
-  int32_t max_batch;                     /* images processed per internal chunk (workspace sizing); 0 = default */
+  int32_t max_batch;                     /* images per super-chunk / CUDA graph (workspace sizing); 0 = 512 */
   int32_t device;                        /* CUDA device ordinal */
 } parseq_config;
 
@@ -100,7 +100,8 @@ int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* m
 
 /* Introspection used by bench.py / tests. */
 int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count of kernels launched */
-/* Options: "chunk" (images per internal chunk), "timing" (1: record a CUDA-event pair around every launch
+/* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per pipeline stage inside a
+ * super-chunk: stage s decodes on its own stream while stage s+1 is being encoded), "use_graph" (0/1), "timing" (1: record a CUDA-event pair around every launch
  * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests). */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of

@@ -96,6 +96,13 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const pq::GemmP
 
 int g_block_n_override = 0;
 
+int init_kernel_attributes() {   // outside any stream capture
+  if (!g_attr_set[0]) { PQ_CUDA(cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<64>::kSmemBytes)); g_attr_set[0] = true; }
+  if (!g_attr_set[1]) { PQ_CUDA(cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<128>::kSmemBytes)); g_attr_set[1] = true; }
+  if (!g_attr_set[2]) { PQ_CUDA(cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<256>::kSmemBytes)); g_attr_set[2] = true; }
+  return PARSEQ_OK;
+}
+
 int gemm_launch(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                 int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
                 cudaStream_t st) {
@@ -180,16 +187,26 @@ struct parseq_engine {
   // derived tables
   __nv_bfloat16* kvtab = nullptr;   // [L*V, 2D]
   float* qs = nullptr;              // [L, D]
-  // workspace (chunk images)
-  __nv_bfloat16 *a_pe = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *mem = nullptr,
-                *ckv = nullptr;
+  // encoder workspace (one pipeline stage = `chunk` images; the encoder runs serialised on `main`)
+  __nv_bfloat16 *a_pe = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
   float* x = nullptr;
-  __nv_bfloat16 *sa = nullptr, *yn = nullptr, *ca = nullptr, *hd = nullptr;
-  float *y = nullptr, *qc = nullptr;
-  int *ids_ar = nullptr, *ids_ctx = nullptr;
-  // host-API staging
-  float* st_images = nullptr; float* st_logits = nullptr; int* st_ids = nullptr; int* st_steps = nullptr;
-  long long st_batch = 0;
+  // per-stage decoder state: the decoder of stage s runs on its own stream while `main` encodes stage s+1
+  struct Stage {
+    __nv_bfloat16 *mem = nullptr, *ckv = nullptr, *sa = nullptr, *yn = nullptr, *ca = nullptr, *hd = nullptr;
+    float *y = nullptr, *qc = nullptr;
+    int *ids_ar = nullptr, *ids_ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_enc = nullptr, ev_done = nullptr;
+  };
+  std::vector<Stage> stages;
+  int max_batch = 512;              // images per graph / super-chunk = stages.size() * chunk
+  cudaStream_t main = nullptr;      // engine-owned: user stream -> (event) -> main -> (event) -> user stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // static I/O buffers the CUDA graphs are captured on
+  float* in_images = nullptr; float* out_logits = nullptr; int* out_ids = nullptr; int* out_steps = nullptr;
+  bool use_graph = true;
+  struct GraphEntry { cudaGraphExec_t exec; long long kernels; };
+  std::map<std::vector<int>, GraphEntry> graphs;
 
   void* w(const std::string& k) const { return slots[index.at(k)].dev; }
   const float* wf(const std::string& k) const { return reinterpret_cast<const float*>(w(k)); }
@@ -219,27 +236,53 @@ int alloc_workspace(parseq_engine* e) {
   PQ_TRY(dev_alloc(&e->qkv, R * 3 * D));
   PQ_TRY(dev_alloc(&e->att, R * D));
   PQ_TRY(dev_alloc(&e->hid, R * e->Me));
-  PQ_TRY(dev_alloc(&e->mem, R * D));
-  PQ_TRY(dev_alloc(&e->ckv, R * 2 * D));
-  PQ_TRY(dev_alloc(&e->sa, Rd * D));
-  PQ_TRY(dev_alloc(&e->yn, Rd * D));
-  PQ_TRY(dev_alloc(&e->ca, Rd * D));
-  PQ_TRY(dev_alloc(&e->hd, Rd * e->Md));
-  PQ_TRY(dev_alloc(&e->y, Rd * D));
-  PQ_TRY(dev_alloc(&e->qc, Rd * D));
-  PQ_TRY(dev_alloc(&e->ids_ar, static_cast<long long>(e->chunk) * 32));
-  PQ_TRY(dev_alloc(&e->ids_ctx, static_cast<long long>(e->chunk) * 32));
+  const int n_stages = (e->max_batch + e->chunk - 1) / e->chunk;
+  e->stages.resize(static_cast<size_t>(n_stages));
+  for (auto& sg : e->stages) {
+    PQ_TRY(dev_alloc(&sg.mem, R * D));
+    PQ_TRY(dev_alloc(&sg.ckv, R * 2 * D));
+    PQ_TRY(dev_alloc(&sg.sa, Rd * D));
+    PQ_TRY(dev_alloc(&sg.yn, Rd * D));
+    PQ_TRY(dev_alloc(&sg.ca, Rd * D));
+    PQ_TRY(dev_alloc(&sg.hd, Rd * e->Md));
+    PQ_TRY(dev_alloc(&sg.y, Rd * D));
+    PQ_TRY(dev_alloc(&sg.qc, Rd * D));
+    PQ_TRY(dev_alloc(&sg.ids_ar, static_cast<long long>(e->chunk) * 32));
+    PQ_TRY(dev_alloc(&sg.ids_ctx, static_cast<long long>(e->chunk) * 32));
+    PQ_CUDA(cudaStreamCreateWithFlags(&sg.stream, cudaStreamNonBlocking));
+    PQ_CUDA(cudaEventCreateWithFlags(&sg.ev_enc, cudaEventDisableTiming));
+    PQ_CUDA(cudaEventCreateWithFlags(&sg.ev_done, cudaEventDisableTiming));
+  }
+  const long long NB = static_cast<long long>(n_stages) * e->chunk;
+  PQ_TRY(dev_alloc(&e->in_images, NB * 3 * e->cfg.img_h * e->cfg.img_w));
+  PQ_TRY(dev_alloc(&e->out_logits, NB * e->L * e->C));
+  PQ_TRY(dev_alloc(&e->out_ids, NB * e->L));
+  PQ_TRY(dev_alloc(&e->out_steps, 4));
   return PARSEQ_OK;
 }
 
+void drop_graphs(parseq_engine* e) {
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+}
+
 void free_workspace(parseq_engine* e) {
-  void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->mem, e->ckv, e->sa, e->yn, e->ca,
-                  e->hd, e->y, e->qc, e->ids_ar, e->ids_ctx};
+  drop_graphs(e);
+  void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->in_images, e->out_logits, e->out_ids, e->out_steps};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  e->a_pe = e->xn = e->qkv = e->att = e->hid = e->mem = e->ckv = e->sa = e->yn = e->ca = e->hd = nullptr;
-  e->x = e->y = e->qc = nullptr;
-  e->ids_ar = e->ids_ctx = nullptr;
+  e->a_pe = e->xn = e->qkv = e->att = e->hid = nullptr;
+  e->x = e->in_images = e->out_logits = nullptr;
+  e->out_ids = e->out_steps = nullptr;
+  for (auto& sg : e->stages) {
+    void* q[] = {sg.mem, sg.ckv, sg.sa, sg.yn, sg.ca, sg.hd, sg.y, sg.qc, sg.ids_ar, sg.ids_ctx};
+    for (void* p : q)
+      if (p) cudaFree(p);
+    if (sg.stream) cudaStreamDestroy(sg.stream);
+    if (sg.ev_enc) cudaEventDestroy(sg.ev_enc);
+    if (sg.ev_done) cudaEventDestroy(sg.ev_done);
+  }
+  e->stages.clear();
 }
 
 // categories: 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other
@@ -275,7 +318,8 @@ int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float
 }
 
 // ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
-int encode_chunk(parseq_engine* e, const float* images, int B, float* memory32, cudaStream_t st) {
+int encode_chunk(parseq_engine* e, const float* images, int B, __nv_bfloat16* mem_out, float* memory32,
+                 cudaStream_t st) {
   const int D = e->D, T = e->T, M = B * T;
   e->cur_cat = CAT_ENC_GEMM;
   {
@@ -307,14 +351,14 @@ int encode_chunk(parseq_engine* e, const float* images, int B, float* memory32, 
     PQ_TRY(gemm(e, e->hid, e->Me, e->w(p + "mlp.fc2.weight"), e->Me, e->wf(p + "mlp.fc2.bias"), M, D, e->Me,
                 pq::EPI_F32, 1.0f, e->x, D, 0, e->x, D, st));
   }
-  PQ_TRY(layernorm(e, e->x, "encoder.norm", 1e-6f, M, e->mem, memory32, st));
+  PQ_TRY(layernorm(e, e->x, "encoder.norm", 1e-6f, M, mem_out, memory32, st));
   return PARSEQ_OK;
 }
 
 // ---------------------------------------------------------------- one Decoder call (model.py:86-103, modules.py:55-125)
 // rows are (b, qi), qi in [0,nq); query position q0+qi; context ids[b, 0..nkeys-1].
-int decode_pass(parseq_engine* e, int B, int nq, int q0, int nkeys, int mode, const int* ids, float* logits_out,
-                long long logits_ld, cudaStream_t st) {
+int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int B, int nq, int q0, int nkeys, int mode, const int* ids,
+                float* logits_out, long long logits_ld, cudaStream_t st) {
   const int D = e->D, M = B * nq;
   const std::string Ly = "decoder.layers.0.";
   const float qscale = 1.0f / std::sqrt(static_cast<float>(e->dh_dec));
@@ -323,35 +367,35 @@ int decode_pass(parseq_engine* e, int B, int nq, int q0, int nkeys, int mode, co
   e->cur_cat = CAT_DEC_GEMM;
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
-    pq::dec_self_attn_kernel<<<M, D, 0, st>>>(e->qs, e->kvtab, ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, e->sa);
+    pq::dec_self_attn_kernel<<<M, D, 0, st>>>(e->qs, e->kvtab, ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa);
     PQ_CUDA(cudaGetLastError());
   }
   const float* posq = e->wf("pos_queries") + static_cast<long long>(q0) * D;
-  PQ_TRY(gemm(e, e->sa, D, e->w(Ly + "self_attn.out_proj.weight"), D, e->wf(Ly + "self_attn.out_proj.bias"), M, D, D,
-              pq::EPI_F32, 1.0f, posq, D, nq, e->y, D, st));
-  PQ_TRY(layernorm(e, e->y, Ly + "norm1", 1e-5f, M, e->yn, nullptr, st));
-  PQ_TRY(gemm(e, e->yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, e->qc, D, st));
+  PQ_TRY(gemm(e, sg.sa, D, e->w(Ly + "self_attn.out_proj.weight"), D, e->wf(Ly + "self_attn.out_proj.bias"), M, D, D,
+              pq::EPI_F32, 1.0f, posq, D, nq, sg.y, D, st));
+  PQ_TRY(layernorm(e, sg.y, Ly + "norm1", 1e-5f, M, sg.yn, nullptr, st));
+  PQ_TRY(gemm(e, sg.yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, sg.qc, D, st));
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
     const int heads = e->cfg.dec_num_heads;
     if (e->T <= 128) {
       const size_t sm = static_cast<size_t>(heads) * (32 + 128) * sizeof(float);
-      pq::dec_cross_attn_kernel<128><<<M, D, sm, st>>>(e->qc, e->ckv, e->T, D, nq, e->ca);
+      pq::dec_cross_attn_kernel<128><<<M, D, sm, st>>>(sg.qc, sg.ckv, e->T, D, nq, sg.ca);
     } else {
       const size_t sm = static_cast<size_t>(heads) * (32 + 256) * sizeof(float);
-      pq::dec_cross_attn_kernel<256><<<M, D, sm, st>>>(e->qc, e->ckv, e->T, D, nq, e->ca);
+      pq::dec_cross_attn_kernel<256><<<M, D, sm, st>>>(sg.qc, sg.ckv, e->T, D, nq, sg.ca);
     }
     PQ_CUDA(cudaGetLastError());
   }
-  PQ_TRY(gemm(e, e->ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
-              pq::EPI_F32, 1.0f, e->y, D, 0, e->y, D, st));
-  PQ_TRY(layernorm(e, e->y, Ly + "norm2", 1e-5f, M, e->yn, nullptr, st));
-  PQ_TRY(gemm(e, e->yn, D, e->w(Ly + "linear1.weight"), D, e->wf(Ly + "linear1.bias"), M, e->Md, D, pq::EPI_GELU_BF16,
-              1.0f, nullptr, 0, 0, e->hd, e->Md, st));
-  PQ_TRY(gemm(e, e->hd, e->Md, e->w(Ly + "linear2.weight"), e->Md, e->wf(Ly + "linear2.bias"), M, D, e->Md, pq::EPI_F32,
-              1.0f, e->y, D, 0, e->y, D, st));
-  PQ_TRY(layernorm(e, e->y, "decoder.norm", 1e-5f, M, e->yn, nullptr, st));
-  PQ_TRY(gemm(e, e->yn, D, e->w("head.weight"), D, e->wf("head.bias"), M, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0,
+  PQ_TRY(gemm(e, sg.ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
+              pq::EPI_F32, 1.0f, sg.y, D, 0, sg.y, D, st));
+  PQ_TRY(layernorm(e, sg.y, Ly + "norm2", 1e-5f, M, sg.yn, nullptr, st));
+  PQ_TRY(gemm(e, sg.yn, D, e->w(Ly + "linear1.weight"), D, e->wf(Ly + "linear1.bias"), M, e->Md, D, pq::EPI_GELU_BF16,
+              1.0f, nullptr, 0, 0, sg.hd, e->Md, st));
+  PQ_TRY(gemm(e, sg.hd, e->Md, e->w(Ly + "linear2.weight"), e->Md, e->wf(Ly + "linear2.bias"), M, D, e->Md, pq::EPI_F32,
+              1.0f, sg.y, D, 0, sg.y, D, st));
+  PQ_TRY(layernorm(e, sg.y, "decoder.norm", 1e-5f, M, sg.yn, nullptr, st));
+  PQ_TRY(gemm(e, sg.yn, D, e->w("head.weight"), D, e->wf("head.bias"), M, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0,
               logits_out, logits_ld, st));
   return PARSEQ_OK;
 }
@@ -367,53 +411,155 @@ int argmax_rows(parseq_engine* e, const float* logits, int L, int B, int nrows, 
   return PARSEQ_OK;
 }
 
-int forward_chunk(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const float* images,
-                  float* logits, int* ids_out, int* steps, cudaStream_t st) {
+// Decoder half of one pipeline stage (B <= chunk images whose memory is in sg.mem): cross K/V projection,
+// AR loop / NAR pass, cloze refinement, final argmax.  model.py:113-169.
+int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const parseq_forward_args* a, int b0, int B, int L,
+                 float* logits, int* ids_out, int* steps, cudaStream_t st) {
   const int D = e->D, T = e->T, C = e->C;
   const int bos = e->V - 2, pad = e->V - 1;
   const bool testing = a->max_length < 0;
-  PQ_TRY(encode_chunk(e, images, B, nullptr, st));
-  // cross-attention K/V of the image memory, once per image (reference recomputes it in every decode call)
+  // cross-attention K/V of the image memory, once per image (the reference recomputes it in every decode call)
   e->cur_cat = CAT_DEC_GEMM;
   {
     const std::string Ly = "decoder.layers.0.";
     const __nv_bfloat16* Wkv = e->wb(Ly + "cross_attn.in_proj_weight") + static_cast<long long>(D) * D;
     const float* bkv = e->wf(Ly + "cross_attn.in_proj_bias") + D;
-    PQ_TRY(gemm(e, e->mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, e->ckv, 2 * D, st));
+    PQ_TRY(gemm(e, sg.mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, sg.ckv, 2 * D, st));
   }
   const long long LC = static_cast<long long>(L) * C;
   if (a->decode_ar) {
-    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->ids_ar, B, 32, bos, pad);
+    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(sg.ids_ar, B, 32, bos, pad);
     PQ_CUDA(cudaGetLastError());
     e->launches++;
     const int* forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
     for (int i = 0; i < L; ++i) {
-      PQ_TRY(decode_pass(e, B, 1, i, i + 1, 0, e->ids_ar, logits + static_cast<long long>(i) * C, LC, st));
-      if (i + 1 < L) PQ_TRY(argmax_rows(e, logits, L, B, 1, i, e->ids_ar, 32, i + 1, forced, L, st));
+      PQ_TRY(decode_pass(e, sg, B, 1, i, i + 1, 0, sg.ids_ar, logits + static_cast<long long>(i) * C, LC, st));
+      if (i + 1 < L) PQ_TRY(argmax_rows(e, logits, L, B, 1, i, sg.ids_ar, 32, i + 1, forced, L, st));
     }
     if (testing && steps != nullptr) {
-      pq::ar_steps_kernel<<<1, 256, 0, st>>>(e->ids_ar, 32, B, L, 0, steps);
+      pq::ar_steps_kernel<<<1, 256, 0, st>>>(sg.ids_ar, 32, B, L, 0, steps);
       PQ_CUDA(cudaGetLastError());
       e->launches++;
     }
   } else {
-    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->ids_ctx, B, 32, bos, pad);
+    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(sg.ids_ctx, B, 32, bos, pad);
     PQ_CUDA(cudaGetLastError());
     e->launches++;
-    PQ_TRY(decode_pass(e, B, L, 0, 1, 0, e->ids_ctx, logits, C, st));
+    PQ_TRY(decode_pass(e, sg, B, L, 0, 1, 0, sg.ids_ctx, logits, C, st));
   }
   for (int it = 0; it < a->refine_iters; ++it) {
-    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(e->ids_ctx, B, 32, bos, pad);
+    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(sg.ids_ctx, B, 32, bos, pad);
     PQ_CUDA(cudaGetLastError());
     e->launches++;
     const int* forced = a->forced_refine
                             ? a->forced_refine + (static_cast<long long>(it) * a->batch + b0) * L
                             : nullptr;
     // ctx = [BOS, argmax(logits[:, :L-1])]  (model.py:161)
-    PQ_TRY(argmax_rows(e, logits, L, B, L - 1, 0, e->ids_ctx, 32, 1, forced, L, st));
-    PQ_TRY(decode_pass(e, B, L, 0, L, 1, e->ids_ctx, logits, C, st));
+    PQ_TRY(argmax_rows(e, logits, L, B, L - 1, 0, sg.ids_ctx, 32, 1, forced, L, st));
+    PQ_TRY(decode_pass(e, sg, B, L, 0, L, 1, sg.ids_ctx, logits, C, st));
   }
   if (ids_out != nullptr) PQ_TRY(argmax_rows(e, logits, L, B, L, 0, ids_out, L, 0, nullptr, 0, st));
+  return PARSEQ_OK;
+}
+
+// One super-chunk (B <= max_batch images) as a software pipeline over stages of `chunk` images:
+// `main` encodes stage s, then stage s's decoder (a latency-bound chain of small kernels) runs on the stage's
+// own stream while `main` already encodes stage s+1.  Fork/join with events (capturable into a CUDA graph).
+int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const float* images,
+                  float* logits, int* ids_out, int* steps) {
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  const int n = (B + e->chunk - 1) / e->chunk;
+  for (int s = 0; s < n; ++s) {
+    parseq_engine::Stage& sg = e->stages[static_cast<size_t>(s)];
+    const int o = s * e->chunk;
+    const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
+    PQ_TRY(encode_chunk(e, images + o * img_sz, Bs, sg.mem, nullptr, e->main));
+    const bool fork = (n > 1) && !e->timing;   // timing mode: everything on `main` (isolated kernel times)
+    cudaStream_t ds = fork ? sg.stream : e->main;
+    if (fork) {
+      PQ_CUDA(cudaEventRecord(sg.ev_enc, e->main));
+      PQ_CUDA(cudaStreamWaitEvent(ds, sg.ev_enc, 0));
+    }
+    PQ_TRY(decode_stage(e, sg, a, b0 + o, Bs, L, logits + 1ll * o * L * e->C, ids_out ? ids_out + 1ll * o * L : nullptr,
+                        steps, ds));
+    if (fork) PQ_CUDA(cudaEventRecord(sg.ev_done, ds));
+  }
+  if (n > 1 && !e->timing)
+    for (int s = 0; s < n; ++s) PQ_CUDA(cudaStreamWaitEvent(e->main, e->stages[static_cast<size_t>(s)].ev_done, 0));
+  return PARSEQ_OK;
+}
+
+int num_steps_of(const parseq_engine* e, int max_length) {
+  const int ml = (max_length < 0) ? e->cfg.max_label_length
+                                  : (max_length < e->cfg.max_label_length ? max_length : e->cfg.max_label_length);
+  return ml + 1;
+}
+
+// Replays (capturing on first use) the CUDA graph of one super-chunk of Bc images on the static I/O buffers.
+int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L) {
+  std::vector<int> key = {Bc, L, a->max_length < 0 ? 1 : 0, a->decode_ar ? 1 : 0, a->refine_iters};
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    parseq_forward_args aa = *a;
+    aa.batch = Bc;
+    aa.forced_ids = nullptr;
+    aa.forced_refine = nullptr;
+    const long long before = e->launches;
+    PQ_CUDA(cudaStreamBeginCapture(e->main, cudaStreamCaptureModeThreadLocal));
+    int r = forward_super(e, &aa, 0, Bc, L, e->in_images, e->out_logits, e->out_ids, e->out_steps);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(e->main, &g);
+    if (r != PARSEQ_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (ce != cudaSuccess) return fail(PARSEQ_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(PARSEQ_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+    parseq_engine::GraphEntry ge{exec, e->launches - before};
+    e->launches = before;
+    it = e->graphs.emplace(key, ge).first;
+  }
+  PQ_CUDA(cudaGraphLaunch(it->second.exec, e->main));
+  e->launches += it->second.kernels;
+  return PARSEQ_OK;
+}
+
+// Common driver of parseq_forward / parseq_forward_host. `host` selects H2D/D2H vs D2D staging copies.
+int forward_impl(parseq_engine* e, const parseq_forward_args* a, const float* images, float* logits, int32_t* ids,
+                 int32_t* steps, cudaStream_t user, bool host) {
+  const int L = num_steps_of(e, a->max_length);
+  const bool testing = a->max_length < 0;
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  const bool eager = !e->use_graph || e->timing || a->forced_ids != nullptr || a->forced_refine != nullptr;
+  const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const cudaMemcpyKind kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  // user stream -> main
+  PQ_CUDA(cudaEventRecord(e->ev_in, user));
+  PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
+  pq::set_int_kernel<<<1, 32, 0, e->main>>>(e->out_steps, (testing && a->decode_ar) ? 0 : L);
+  PQ_CUDA(cudaGetLastError());
+  e->launches++;
+  for (int b0 = 0; b0 < a->batch; b0 += e->max_batch) {
+    const int Bc = (a->batch - b0 < e->max_batch) ? (a->batch - b0) : e->max_batch;
+    if (eager && !host) {
+      PQ_TRY(forward_super(e, a, b0, Bc, L, images + b0 * img_sz, logits + 1ll * b0 * L * e->C,
+                           ids ? ids + 1ll * b0 * L : nullptr, e->out_steps));
+      continue;
+    }
+    PQ_CUDA(cudaMemcpyAsync(e->in_images, images + b0 * img_sz, static_cast<size_t>(Bc * img_sz) * 4, kin, e->main));
+    if (eager) {
+      PQ_TRY(forward_super(e, a, b0, Bc, L, e->in_images, e->out_logits, e->out_ids, e->out_steps));
+    } else {
+      PQ_TRY(run_graph(e, a, Bc, L));
+    }
+    PQ_CUDA(cudaMemcpyAsync(logits + 1ll * b0 * L * e->C, e->out_logits, static_cast<size_t>(1ll * Bc * L * e->C) * 4, kout,
+                            e->main));
+    if (ids) PQ_CUDA(cudaMemcpyAsync(ids + 1ll * b0 * L, e->out_ids, static_cast<size_t>(1ll * Bc * L) * 4, kout, e->main));
+  }
+  if (steps) PQ_CUDA(cudaMemcpyAsync(steps, e->out_steps, 4, kout, e->main));
+  // main -> user stream
+  PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
+  PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
   return PARSEQ_OK;
 }
 
@@ -439,6 +585,8 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
     return fail(PARSEQ_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                           ", the kernels are sm_100a (B200) only");
   g_sm_count = prop.multiProcessorCount;
+  PQ_TRY(init_kernel_attributes());
+  PQ_TRY(load_driver_api());
   if (cfg->dec_depth != 1) return fail(PARSEQ_ERR_UNSUPPORTED, "dec_depth must be 1");
   if (cfg->img_h % cfg->patch_h || cfg->img_w % cfg->patch_w) return fail(PARSEQ_ERR_INVALID_ARG, "img/patch mismatch");
   const int D = cfg->embed_dim;
@@ -459,7 +607,8 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   e->V = cfg->num_tokens;
   e->C = cfg->num_tokens - 2;
   e->dh_dec = D / cfg->dec_num_heads;
-  e->chunk = cfg->max_batch > 0 ? cfg->max_batch : 128;
+  e->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 512;
+  e->chunk = e->max_batch < 128 ? e->max_batch : 128;
   if (e->T != 128) {
     delete e;
     return fail(PARSEQ_ERR_UNSUPPORTED, "this build covers 128-token images (32x128 / patch 4x8)");
@@ -517,6 +666,10 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   int r = dev_alloc(&e->kvtab, 1ll * e->L * e->V * 2 * D);
   if (r == PARSEQ_OK) r = dev_alloc(&e->qs, 1ll * e->L * D);
   if (r == PARSEQ_OK) r = alloc_workspace(e);
+  if (r == PARSEQ_OK && cudaStreamCreateWithFlags(&e->main, cudaStreamNonBlocking) != cudaSuccess) r = fail(PARSEQ_ERR_CUDA, "stream");
+  if (r == PARSEQ_OK && (cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess))
+    r = fail(PARSEQ_ERR_CUDA, "event");
   if (r != PARSEQ_OK) { parseq_destroy(e); return r; }
   *out = e;
   return PARSEQ_OK;
@@ -531,10 +684,11 @@ void parseq_destroy(parseq_engine* e) {
   if (e->kvtab) cudaFree(e->kvtab);
   if (e->qs) cudaFree(e->qs);
   free_workspace(e);
-  if (e->st_images) cudaFree(e->st_images);
-  if (e->st_logits) cudaFree(e->st_logits);
-  if (e->st_ids) cudaFree(e->st_ids);
-  if (e->st_steps) cudaFree(e->st_steps);
+  if (e->main) cudaStreamDestroy(e->main);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  for (auto& t : e->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto ev : e->event_pool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -616,55 +770,22 @@ int parseq_forward(parseq_engine* e, const parseq_forward_args* a, const float* 
   if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
   if (a->batch == 0) return PARSEQ_OK;
   PQ_CUDA(cudaSetDevice(e->cfg.device));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int maxlen = (a->max_length < 0) ? e->cfg.max_label_length
-                                         : (a->max_length < e->cfg.max_label_length ? a->max_length : e->cfg.max_label_length);
-  const int L = maxlen + 1;
-  const bool testing = a->max_length < 0;
-  if (steps != nullptr) {
-    pq::set_int_kernel<<<1, 32, 0, st>>>(steps, (testing && a->decode_ar) ? 0 : L);
-    PQ_CUDA(cudaGetLastError());
-    e->launches++;
-  }
-  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
-  for (int b0 = 0; b0 < a->batch; b0 += e->chunk) {
-    const int B = (a->batch - b0 < e->chunk) ? (a->batch - b0) : e->chunk;
-    PQ_TRY(forward_chunk(e, a, b0, B, L, images + b0 * img_sz, logits + 1ll * b0 * L * e->C,
-                         ids ? ids + 1ll * b0 * L : nullptr, steps, st));
-  }
-  return PARSEQ_OK;
+  return forward_impl(e, a, images, logits, ids, steps, reinterpret_cast<cudaStream_t>(stream), false);
 }
 
 int parseq_forward_host(parseq_engine* e, const parseq_forward_args* a, const float* images_host, float* logits_host,
                         int32_t* ids_host, int32_t* steps_host, parseq_stream_t stream) {
   if (e == nullptr || a == nullptr || images_host == nullptr || logits_host == nullptr)
     return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
+  if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
+  if (a->batch == 0) return PARSEQ_OK;
+  if (a->forced_ids != nullptr || a->forced_refine != nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "teacher forcing is a device-pointer API (parseq_forward)");
   PQ_CUDA(cudaSetDevice(e->cfg.device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long B = a->batch;
-  if (B <= 0) return B == 0 ? PARSEQ_OK : fail(PARSEQ_ERR_INVALID_ARG, "negative batch");
-  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
-  if (B > e->st_batch) {
-    if (e->st_images) cudaFree(e->st_images);
-    if (e->st_logits) cudaFree(e->st_logits);
-    if (e->st_ids) cudaFree(e->st_ids);
-    if (e->st_steps) cudaFree(e->st_steps);
-    e->st_images = nullptr; e->st_logits = nullptr; e->st_ids = nullptr; e->st_steps = nullptr; e->st_batch = 0;
-    PQ_TRY(dev_alloc(&e->st_images, B * img_sz));
-    PQ_TRY(dev_alloc(&e->st_logits, B * e->L * e->C));
-    PQ_TRY(dev_alloc(&e->st_ids, B * e->L));
-    PQ_TRY(dev_alloc(&e->st_steps, 4));
-    e->st_batch = B;
-  }
-  const int maxlen = (a->max_length < 0) ? e->cfg.max_label_length
-                                         : (a->max_length < e->cfg.max_label_length ? a->max_length : e->cfg.max_label_length);
-  const long long L = maxlen + 1;
-  PQ_CUDA(cudaMemcpyAsync(e->st_images, images_host, static_cast<size_t>(B * img_sz) * 4, cudaMemcpyHostToDevice, st));
-  PQ_TRY(parseq_forward(e, a, e->st_images, e->st_logits, e->st_ids, e->st_steps, stream));
-  PQ_CUDA(cudaMemcpyAsync(logits_host, e->st_logits, static_cast<size_t>(B * L * e->C) * 4, cudaMemcpyDeviceToHost, st));
-  if (ids_host) PQ_CUDA(cudaMemcpyAsync(ids_host, e->st_ids, static_cast<size_t>(B * L) * 4, cudaMemcpyDeviceToHost, st));
-  if (steps_host) PQ_CUDA(cudaMemcpyAsync(steps_host, e->st_steps, 4, cudaMemcpyDeviceToHost, st));
-  PQ_CUDA(cudaStreamSynchronize(st));
+  PQ_TRY(forward_impl(e, a, images_host, logits_host, ids_host, steps_host, st, true));
+  PQ_CUDA(cudaStreamSynchronize(e->main));
   return PARSEQ_OK;
 }
 
@@ -672,12 +793,16 @@ int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* m
   if (e == nullptr || images == nullptr || memory == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called");
   PQ_CUDA(cudaSetDevice(e->cfg.device));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  PQ_CUDA(cudaEventRecord(e->ev_in, user));
+  PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
   const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
   for (int b0 = 0; b0 < batch; b0 += e->chunk) {
     const int B = (batch - b0 < e->chunk) ? (batch - b0) : e->chunk;
-    PQ_TRY(encode_chunk(e, images + b0 * img_sz, B, memory + 1ll * b0 * e->T * e->D, st));
+    PQ_TRY(encode_chunk(e, images + b0 * img_sz, B, e->stages[0].mem, memory + 1ll * b0 * e->T * e->D, e->main));
   }
+  PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
+  PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
   return PARSEQ_OK;
 }
 
@@ -698,12 +823,15 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     e->timed.clear();
     return PARSEQ_OK;
   }
-  if (n == "chunk") {
-    if (value <= 0 || value > 4096) return fail(PARSEQ_ERR_INVALID_ARG, "chunk out of range");
+  if (n == "use_graph") { e->use_graph = value != 0; return PARSEQ_OK; }
+  if (n == "chunk" || n == "max_batch") {
+    if (value <= 0 || value > 8192) return fail(PARSEQ_ERR_INVALID_ARG, "chunk / max_batch out of range");
     PQ_CUDA(cudaSetDevice(e->cfg.device));
     PQ_CUDA(cudaDeviceSynchronize());
     free_workspace(e);
-    e->chunk = static_cast<int>(value);
+    if (n == "chunk") e->chunk = static_cast<int>(value); else e->max_batch = static_cast<int>(value);
+    if (e->chunk > e->max_batch) e->chunk = e->max_batch;
+    if ((e->max_batch + e->chunk - 1) / e->chunk > 64) return fail(PARSEQ_ERR_INVALID_ARG, "too many pipeline stages");
     return alloc_workspace(e);
   }
   return fail(PARSEQ_ERR_INVALID_ARG, "unknown option: " + n);

@@ -82,12 +82,12 @@ def check(lib, rc: int):
 class Engine:
     """Owns one `parseq_engine*`."""
 
-    def __init__(self, cfg, device: int = 0, chunk: int = 0):
+    def __init__(self, cfg, device: int = 0, max_batch: int = 0):
         self.lib = load_library()
         self.cfg = cfg
         c = ParseqConfigC(cfg.img_size[0], cfg.img_size[1], cfg.patch_size[0], cfg.patch_size[1], cfg.embed_dim,
                           cfg.enc_num_heads, cfg.enc_mlp_ratio, cfg.enc_depth, cfg.dec_num_heads, cfg.dec_mlp_ratio,
-                          cfg.dec_depth, cfg.max_label_length, cfg.num_tokens, chunk, device)
+                          cfg.dec_depth, cfg.max_label_length, cfg.num_tokens, max_batch, device)
         h = C.c_void_p()
         check(self.lib, self.lib.parseq_create(C.byref(c), C.byref(h)))
         self.handle = h

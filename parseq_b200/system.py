@@ -81,7 +81,7 @@ class ParseqModel(nn.Module):
             _register(self, k, v)
         self._engine: Optional[Engine] = None
         self._engine_sig = None
-        self._chunk = 0
+        self._options = {}
 
     # ---- engine plumbing -------------------------------------------------------------------
     @property
@@ -98,7 +98,9 @@ class ParseqModel(nn.Module):
                                "— there is no CPU fallback")
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         if self._engine is None or self._engine.device != idx:
-            self._engine = Engine(self.cfg, idx, self._chunk)
+            self._engine = Engine(self.cfg, idx)
+            for name, value in self._options.items():
+                self._engine.set_option(name, value)
             self._engine_sig = None
         sig = self._signature()
         if sig != self._engine_sig:
@@ -106,10 +108,11 @@ class ParseqModel(nn.Module):
             self._engine_sig = sig
         return self._engine
 
-    def set_chunk(self, chunk: int):
-        self._chunk = int(chunk)
+    def set_engine_option(self, name: str, value: int):
+        """Engine tuning knobs: "max_batch", "chunk", "use_graph" (see include/parseq_b200.h)."""
+        self._options[name] = int(value)
         if self._engine is not None:
-            self._engine.set_option("chunk", chunk)
+            self._engine.set_option(name, value)
 
     def _check_images(self, images: Tensor) -> Tensor:
         if images.device.type != "cuda":
