@@ -54,16 +54,19 @@ int load_driver_api() {
   return PARSEQ_OK;
 }
 
-// 2D bf16 tensor map: rows x cols (cols contiguous), row stride ld elements, box = box_rows x 64 cols, 128B swizzle.
-int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// 2D tensor map: rows x cols (cols contiguous), row stride ld elements, box = box_rows x box_cols (box_cols * esize
+// = 128 B), 128B swizzle.  esize 2 = bf16, 4 = fp32.
+int make_tmap(CUtensorMap* tm, const void* ptr, int esize, long long rows, long long cols, long long ld, int box_cols,
+              int box_rows) {
   PQ_TRY(load_driver_api());
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ((ld * 2) & 15) != 0)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ((ld * esize) & 15) != 0)
     return fail(PARSEQ_ERR_INVALID_ARG, "GEMM operand must be 16-byte aligned with a 16-byte multiple row stride");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(pq::GEMM_BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * static_cast<cuuint64_t>(esize)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(tm, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PARSEQ_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
@@ -79,27 +82,52 @@ uint16_t f32_to_bf16_rne(float f) {
 }
 
 int g_sm_count = 0;
-bool g_attr_set[3] = {false, false, false};
+int g_block_n_override = 0;
+int g_cta_group_override = 0;   // 0 = auto, 1 / 2 = forced (tests)
+bool g_no_tma_epilogue = false; // tests: force the direct-store epilogue
 
-template <int BN>
-int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const pq::GemmParams& p, int grid, cudaStream_t st,
-                   int slot) {
-  auto kern = pq::gemm_bf16_tcgen05_kernel<BN>;
-  if (!g_attr_set[slot]) {
-    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<BN>::kSmemBytes));
-    g_attr_set[slot] = true;
+template <int BN, int CG>
+int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const pq::GemmParams& p, int tiles,
+                    cudaStream_t st) {
+  auto kern = pq::gemm_bf16_tcgen05_kernel<BN, CG>;
+  using Cfg = pq::GemmCfg<BN, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
   }
-  kern<<<grid, pq::GEMM_THREADS, pq::GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
-  PQ_CUDA(cudaGetLastError());
+  const int max_groups = g_sm_count / CG;
+  const int groups = tiles < max_groups ? tiles : max_groups;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
+  cfg.blockDim = dim3(pq::GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return PARSEQ_OK;
 }
 
-int g_block_n_override = 0;
-
-int init_kernel_attributes() {   // outside any stream capture
-  if (!g_attr_set[0]) { PQ_CUDA(cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<64>::kSmemBytes)); g_attr_set[0] = true; }
-  if (!g_attr_set[1]) { PQ_CUDA(cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<128>::kSmemBytes)); g_attr_set[1] = true; }
-  if (!g_attr_set[2]) { PQ_CUDA(cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmCfg<256>::kSmemBytes)); g_attr_set[2] = true; }
+// instantiate + set the smem attribute of every configuration outside of any stream capture
+template <int BN, int CG>
+int warm_gemm_cfg() {
+  return cudaFuncSetAttribute(pq::gemm_bf16_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pq::GemmCfg<BN, CG>::kSmemBytes) == cudaSuccess ? PARSEQ_OK
+                                                                                : fail(PARSEQ_ERR_CUDA, "cudaFuncSetAttribute(gemm)");
+}
+int init_kernel_attributes() {
+  PQ_TRY((warm_gemm_cfg<64, 1>()));
+  PQ_TRY((warm_gemm_cfg<128, 1>()));
+  PQ_TRY((warm_gemm_cfg<256, 1>()));
+  PQ_TRY((warm_gemm_cfg<128, 2>()));
+  PQ_TRY((warm_gemm_cfg<192, 2>()));
+  PQ_TRY((warm_gemm_cfg<256, 2>()));
   return PARSEQ_OK;
 }
 
@@ -112,13 +140,22 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
     PQ_CUDA(cudaGetDevice(&dev));
     PQ_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  int BN = 128;
-  if (g_block_n_override) BN = g_block_n_override;
-  else if (N % 256 == 0 && static_cast<long long>((M + 127) / 128) * (N / 256) >= 2ll * g_sm_count) BN = 256;
-  else if (N <= 64) BN = 64;
-  CUtensorMap ta, tb;
-  PQ_TRY(make_tmap_bf16(&ta, A, M, K, lda, pq::GEMM_BLOCK_M));
-  PQ_TRY(make_tmap_bf16(&tb, W, N, K, ldw, BN));
+  // Tile choice from tests/bench_gemm.py on B200 (profiles/r1_gemm_microbench.txt): single-CTA 128 x 256 tiles win
+  // for the wide projections (QKV 1152 -> 4.5 tiles, fc1 1536, fc2/K=1536), 128 x 128 for N = 384 and for the small
+  // decoder GEMMs; the CTA-pair variant (cta_group::2) is correct but slower with this pipeline depth, so it is opt-in.
+  int CG = 1;
+  if (g_cta_group_override) CG = g_cta_group_override;
+  int BN;
+  if (CG == 2) BN = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : 128;
+  else BN = (N <= 64) ? 64 : (M >= 1024 && (N >= 1024 || (N % 256 == 0 && K >= 1024))) ? 256 : 128;
+  if (g_block_n_override) {
+    BN = g_block_n_override;
+    if (CG == 2 && BN == 64) BN = 128;
+    if (CG == 1 && BN == 192) BN = 128;
+  }
+  CUtensorMap ta, tb, tc;
+  PQ_TRY(make_tmap(&ta, A, 2, M, K, lda, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
+  PQ_TRY(make_tmap(&tb, W, 2, N, K, ldw, pq::GEMM_BLOCK_K, BN / CG));
   pq::GemmParams p;
   p.M = M; p.N = N; p.K = K; p.mode = mode; p.alpha = alpha; p.bias = bias;
   p.resid = resid; p.ldr = ldr; p.resid_mod = resid_mod; p.out = out; p.ldo = ldo;
@@ -127,13 +164,29 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
   if (resid != nullptr) vec = vec && ((reinterpret_cast<uintptr_t>(resid) & 15u) == 0) && ((ldr * 4) % 16 == 0);
   if (bias != nullptr) vec = vec && ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0);
   p.vec_ok = vec ? 1 : 0;
-  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
+  // asynchronous TMA epilogue whenever the output is TMA-addressable; residual only as in-place accumulate
+  p.tma_out = 0;
+  const bool out_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((ldo * esz) % 16 == 0) && !g_no_tma_epilogue;
+  if (out_ok) {
+    if (mode != pq::EPI_F32) p.tma_out = 3;
+    else if (resid == nullptr) p.tma_out = 1;
+    else if (resid == out && ldr == ldo && resid_mod == 0) p.tma_out = 2;
+  }
+  if (p.tma_out == 3) PQ_TRY(make_tmap(&tc, out, 2, M, N, ldo, 64, 32));
+  else if (p.tma_out != 0) PQ_TRY(make_tmap(&tc, out, 4, M, N, ldo, 32, 32));
+  else tc = ta;
+  const int tile_m = pq::GEMM_BLOCK_M * CG;
+  p.num_m_tiles = (M + tile_m - 1) / tile_m;
   p.num_n_tiles = (N + BN - 1) / BN;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-  if (BN == 256) return launch_gemm_bn<256>(ta, tb, p, grid, st, 2);
-  if (BN == 64) return launch_gemm_bn<64>(ta, tb, p, grid, st, 0);
-  return launch_gemm_bn<128>(ta, tb, p, grid, st, 1);
+  if (CG == 2) {
+    if (BN == 256) return launch_gemm_cfg<256, 2>(ta, tb, tc, p, tiles, st);
+    if (BN == 192) return launch_gemm_cfg<192, 2>(ta, tb, tc, p, tiles, st);
+    return launch_gemm_cfg<128, 2>(ta, tb, tc, p, tiles, st);
+  }
+  if (BN == 256) return launch_gemm_cfg<256, 1>(ta, tb, tc, p, tiles, st);
+  if (BN == 64) return launch_gemm_cfg<64, 1>(ta, tb, tc, p, tiles, st);
+  return launch_gemm_cfg<128, 1>(ta, tb, tc, p, tiles, st);
 }
 
 int layernorm_launch(const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
@@ -608,7 +661,9 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   e->C = cfg->num_tokens - 2;
   e->dh_dec = D / cfg->dec_num_heads;
   e->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 512;
-  e->chunk = e->max_batch < 128 ? e->max_batch : 128;
+  // One pipeline stage per super-chunk by default: measured on B200 the decoder chain is latency-bound and the
+  // encoder GEMMs occupy every SM, so splitting into stages only shrinks the GEMMs ("chunk" option re-enables it).
+  e->chunk = e->max_batch;
   if (e->T != 128) {
     delete e;
     return fail(PARSEQ_ERR_UNSUPPORTED, "this build covers 128-token images (32x128 / patch 4x8)");
@@ -812,8 +867,15 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (name == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null option");
   const std::string n(name);
   if (n == "block_n") {
-    if (value != 0 && value != 64 && value != 128 && value != 256) return fail(PARSEQ_ERR_INVALID_ARG, "block_n: 0/64/128/256");
+    if (value != 0 && value != 64 && value != 128 && value != 192 && value != 256)
+      return fail(PARSEQ_ERR_INVALID_ARG, "block_n: 0/64/128/192/256");
     g_block_n_override = static_cast<int>(value);
+    return PARSEQ_OK;
+  }
+  if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
+  if (n == "cta_group") {
+    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "cta_group: 0 (auto) / 1 / 2");
+    g_cta_group_override = static_cast<int>(value);
     return PARSEQ_OK;
   }
   if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");

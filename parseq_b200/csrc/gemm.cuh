@@ -30,93 +30,286 @@ struct GemmParams {
   void* out;
   long long ldo;       // elements
   int vec_ok;          // 16B-aligned rows: vector stores allowed
-  int num_m_tiles, num_n_tiles;
+  int tma_out;         // 0: direct stores (fallback), 1: TMA store fp32, 2: TMA reduce-add fp32 (out += ...),
+                       // 3: TMA store bf16 (mode EPI_BF16 / EPI_GELU_BF16)
+  int num_m_tiles, num_n_tiles;  // in units of (128 * CG) x BLOCK_N
 };
 
-constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_M = 128;  // rows per CTA (one TMEM lane per row)
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter (warp % 4), alternating 32/64-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..9: epilogue
 
-template <int BLOCK_N>
+// CG = 1: one CTA computes a 128 x BLOCK_N tile.
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BLOCK_N tile: each CTA loads its own
+//         128 rows of A and HALF of the W tile (BLOCK_N/2 rows), the leader issues UMMA M=256; every operand byte
+//         is fetched from L2 and crosses shared memory once per 256 (instead of 128) output rows.
+template <int BLOCK_N, int CG>
 struct GemmCfg {
-  static constexpr int kStages = (BLOCK_N <= 128) ? 6 : 4;
-  static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KB
-  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int kBRows = BLOCK_N / CG;                       // W rows loaded by one CTA
+  static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
+  static constexpr int kBBytes = kBRows * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 2 * 4096;  // per epilogue warp: 2 buffers x (32 rows x 128 B)
+  static constexpr int kBiasBytes = GEMM_EPI_WARPS * BLOCK_N * 4;   // per-warp copy of the tile's bias slice
+  static constexpr int kStagesRaw = (232448 - 1024 - 256 - kEpiStageBytes - kBiasBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(CG == 1 || CG == 2, "CG");
+  static_assert(kBBytes % 1024 == 0, "stage bases must stay 1024-B aligned");
+  static_assert(kStages >= 3, "pipeline depth");
 };
 
+// ------------------------------------------------------------------------------------------------ epilogue bodies
+// One epilogue warp owns 32 accumulator rows (its TMEM lane quarter); the two warps of a quarter alternate chunks.
+// TMA path: TMEM -> registers -> (+bias, activation) -> 128B-swizzled smem slab (32 rows x 128 B) -> TMA store /
+// fp32 reduce-add; out-of-range rows / columns are clipped by the tensor map, nothing is ever loaded from global.
+template <int BLOCK_N, bool REDUCE>
+__device__ __forceinline__ void epi_tma_f32(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, uint8_t* my_stage,
+                                            const float* my_bias, int n0, int row0, int half, int lane, int& it) {
+  // `it` counts this warp's TMA stores over the whole kernel: slab (it & 1) is free once at most one newer store
+  // is still reading its source (bulk_wait_group_read<1>), so the counter must NOT restart per tile.
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+  for (int c = half; c < BLOCK_N / 32; c += 2, ++it) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+    tmem_ld_wait();
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
+    uint8_t* slab = my_stage + (it & 1) * 4096;
+    uint8_t* buf = slab + lane * 128;
+    const float* bb = my_bias + c * 32;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      float4 q;
+      q.x = (__uint_as_float(v[jj * 4 + 0]) + bb[jj * 4 + 0]) * p.alpha;
+      q.y = (__uint_as_float(v[jj * 4 + 1]) + bb[jj * 4 + 1]) * p.alpha;
+      q.z = (__uint_as_float(v[jj * 4 + 2]) + bb[jj * 4 + 2]) * p.alpha;
+      q.w = (__uint_as_float(v[jj * 4 + 3]) + bb[jj * 4 + 3]) * p.alpha;
+      *reinterpret_cast<float4*>(buf + ((static_cast<uint32_t>(jj) ^ sw) << 4)) = q;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (REDUCE) tma_reduce_add_2d(tmC, slab, col0, row0);
+      else tma_store_2d(tmC, slab, col0, row0);
+      bulk_commit_group();
+    }
+  }
+}
+
+template <int BLOCK_N, bool GELU>
+__device__ __forceinline__ void epi_tma_bf16(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, uint8_t* my_stage,
+                                             const float* my_bias, int n0, int row0, int half, int lane, int& it) {
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+  for (int c = half; c < BLOCK_N / 64; c += 2, ++it) {   // 64 bf16 columns = 128 B per row per TMA store
+    const int col0 = n0 + c * 64;
+    if (col0 >= p.N) break;
+    uint8_t* slab = my_stage + (it & 1) * 4096;
+    uint8_t* buf = slab + lane * 128;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 64 + h * 32), v);
+      tmem_ld_wait();
+      if (h == 0) {
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+      }
+      const float* bb = my_bias + c * 64 + h * 32;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float f[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float a = __uint_as_float(v[jj * 8 + t]) + bb[jj * 8 + t];
+          f[t] = GELU ? gelu_erf(a) : a * p.alpha;
+        }
+        uint4 q;
+        q.x = pack_bf16(f[0], f[1]); q.y = pack_bf16(f[2], f[3]);
+        q.z = pack_bf16(f[4], f[5]); q.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(h * 4 + jj) ^ sw) << 4)) = q;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, slab, col0, row0);
+      bulk_commit_group();
+    }
+  }
+}
+
+// Direct-store fallback (outputs that are not TMA-addressable: odd row pitch of the [B,26,95] logits; residual read
+// from a different / broadcast tensor: + pos_embed, + pos_queries).  One accumulator row per thread.
 template <int BLOCK_N>
+__device__ __forceinline__ void epi_direct(const GemmParams& p, uint32_t taddr, int n0, int row, int half) {
+  const long long rrow = (p.resid_mod > 0) ? (row % p.resid_mod) : row;
+#pragma unroll 1
+  for (int c = half; c < BLOCK_N / 32; c += 2) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.N) break;            // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+    tmem_ld_wait();
+    if (row < p.M) {
+      const bool full = p.vec_ok && (col0 + 32 <= p.N);
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias != nullptr) {
+        if (col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+        }
+      }
+      if (p.mode == EPI_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      } else if (p.alpha != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+      }
+      if (p.mode == EPI_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+        const float* r = (p.resid != nullptr) ? (p.resid + rrow * p.ldr + col0) : nullptr;
+        if (full) {
+          if (r != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 x = *reinterpret_cast<const float4*>(r + j);
+              f[j] += x.x; f[j + 1] += x.y; f[j + 2] += x.z; f[j + 3] += x.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) o[j] = f[j] + ((r != nullptr) ? r[j] : 0.0f);
+        }
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            q.x = pack_bf16(f[j], f[j + 1]);
+            q.y = pack_bf16(f[j + 2], f[j + 3]);
+            q.z = pack_bf16(f[j + 4], f[j + 5]);
+            q.w = pack_bf16(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = q;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+        }
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+                         const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = smem_raw + pad;                         // 1024-B aligned (SWIZZLE_128B requirement)
-  uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);         // [kStages] TMA -> MMA
-  uint64_t* empty_bar = full_bar + Cfg::kStages;                       // [kStages] MMA -> TMA
-  uint64_t* tfull_bar = empty_bar + Cfg::kStages;                      // [2] MMA -> epilogue
-  uint64_t* tempty_bar = tfull_bar + 2;                                // [2] epilogue -> MMA
+  uint8_t* epi_base = smem + Cfg::kStages * Cfg::kStageBytes;        // 1024-B aligned staging tiles for TMA stores
+  float* bias_base = reinterpret_cast<float*>(epi_base + Cfg::kEpiStageBytes);
+  uint8_t* bar_base = epi_base + Cfg::kEpiStageBytes + Cfg::kBiasBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);         // [kStages] TMA -> MMA (leader's copy is live)
+  uint64_t* empty_bar = full_bar + Cfg::kStages;                       // [kStages] MMA -> TMA (each CTA its own)
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;                      // [2] MMA -> epilogue (each CTA its own)
+  uint64_t* tempty_bar = tfull_bar + 2;                                // [2] epilogue -> MMA (leader's copy is live)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;    // tiles of (128*CG) x BLOCK_N
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.tma_out) prefetch_tmap(&tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CG);        // leader's arrive.expect_tx (+ the peer producer's remote arrive)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CG);  // one elected lane per epilogue warp of every CTA of the group
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * GEMM_BLOCK_M;
-        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.num_n_tiles) * (GEMM_BLOCK_M * CG) + static_cast<int>(rank) * GEMM_BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if constexpr (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          } else {
+            const uint32_t leader_full = mapa_cluster(smem_u32(&full_bar[stage]), 0u);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::kStageBytes);
+            else mbar_arrive_cluster(leader_full);
+            tma_load_2d_pair(sa, &tmA, leader_full, kb * GEMM_BLOCK_K, m0);
+            tma_load_2d_pair(sb, &tmB, leader_full, kb * GEMM_BLOCK_K, n0);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    // ===================== MMA issuer (single thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
@@ -129,113 +322,71 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      static_cast<uint32_t>((kb | k) != 0));
+            const uint32_t acc = static_cast<uint32_t>((kb | k) != 0);
+            if constexpr (CG == 2)
+              umma_bf16_pair(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, acc);
+            else
+              umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, acc);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in every CTA of the group) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[as]);       // accumulator complete
+        // accumulator complete (signalled to the epilogue warps of every CTA of the group)
+        if constexpr (CG == 2) umma_commit_pair(&tfull_bar[as], 0x3); else umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (8: two per TMEM lane quarter) =====================
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int ew = warp - 2;               // 0..7
+    const int half = ew >> 2;              // which of the alternating column chunks this warp takes
     const int row_in_tile = quarter * 32 + lane;
+    uint8_t* my_stage = epi_base + ew * 8192;
+    float* my_bias = bias_base + ew * BLOCK_N;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * GEMM_BLOCK_M;
+    int store_it = 0;                      // running count of this warp's TMA stores (staging slab parity)
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.num_n_tiles) * (GEMM_BLOCK_M * CG) + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      const int row = m0 + row_in_tile;
+      if (p.tma_out != 0) {                // bias slice of this tile -> this warp's smem copy (before the wait)
+        __syncwarp();
+        for (int j = lane; j < BLOCK_N; j += 32)
+          my_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.0f;
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * BLOCK_N);
-      const long long rrow = (p.resid_mod > 0) ? (row % p.resid_mod) : row;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;            // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
-        tmem_ld_wait();
-        if (row < p.M) {
-          const bool full = p.vec_ok && (col0 + 32 <= p.N);
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-            if (col0 + 32 <= p.N) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if (p.mode == EPI_GELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          } else if (p.alpha != 1.0f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-          }
-          if (p.mode == EPI_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-            const float* r = (p.resid != nullptr) ? (p.resid + rrow * p.ldr + col0) : nullptr;
-            if (full) {
-              if (r != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 x = *reinterpret_cast<const float4*>(r + j);
-                  f[j] += x.x; f[j + 1] += x.y; f[j + 2] += x.z; f[j + 3] += x.w;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = f[j] + ((r != nullptr) ? r[j] : 0.0f);
-            }
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 q;
-                q.x = pack_bf16(f[j], f[j + 1]);
-                q.y = pack_bf16(f[j + 2], f[j + 3]);
-                q.z = pack_bf16(f[j + 4], f[j + 5]);
-                q.w = pack_bf16(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = q;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
-            }
-          }
-        }
+      const int row0 = m0 + quarter * 32;
+      if (p.tma_out == 2) epi_tma_f32<BLOCK_N, true>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+      else if (p.tma_out == 1) epi_tma_f32<BLOCK_N, false>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+      else if (p.tma_out == 3) {
+        if (p.mode == EPI_GELU_BF16) epi_tma_bf16<BLOCK_N, true>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+        else epi_tma_bf16<BLOCK_N, false>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+      } else {
+        epi_direct<BLOCK_N>(p, taddr, n0, m0 + row_in_tile, half);
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);        // 128 arrivals free this accumulator stage
+      __syncwarp();
+      if (lane == 0) {                     // 8*CG warp arrivals free this accumulator stage (leader's barrier)
+        if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[as]), 0u));
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (p.tma_out != 0 && lane == 0) bulk_wait_group<0>();   // all TMA stores of this warp have completed
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // peer smem / barriers stay valid until all are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

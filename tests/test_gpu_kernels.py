@@ -48,13 +48,15 @@ def test_gemm_f32_bias(lib, M, N, K):
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("block_n", [64, 128, 256])
-def test_gemm_block_n_variants(lib, block_n):
+@pytest.mark.parametrize("cta_group,block_n", [(1, 64), (1, 128), (1, 256), (2, 128), (2, 192), (2, 256)])
+@pytest.mark.parametrize("M,N,K", [(700, 1536, 384), (8192, 1152, 384), (1000, 384, 1536), (130, 95, 384)])
+def test_gemm_tile_variants(lib, cta_group, block_n, M, N, K):
+    """Single-CTA tiles and CTA-pair (cta_group::2, UMMA M=256) tiles of every width, ragged M / N."""
     from parseq_b200.engine import check
     check(lib, lib.parseq_set_option(None, b"block_n", block_n))
+    check(lib, lib.parseq_set_option(None, b"cta_group", cta_group))
     try:
-        g = torch.Generator(device="cuda").manual_seed(block_n)
-        M, N, K = 700, 1536, 384
+        g = torch.Generator(device="cuda").manual_seed(block_n + M)
         A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
         W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
         bias = torch.randn((N,), device="cuda", generator=g)
@@ -63,6 +65,31 @@ def test_gemm_block_n_variants(lib, block_n):
         assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
     finally:
         check(lib, lib.parseq_set_option(None, b"block_n", 0))
+        check(lib, lib.parseq_set_option(None, b"cta_group", 0))
+
+
+@pytest.mark.parametrize("N,K,mode", [(1152, 384, 1), (384, 384, 0), (1536, 384, 2), (384, 1536, 0)])
+def test_gemm_deterministic_many_tiles_per_cta(lib, N, K, mode):
+    """Persistent kernel, ~15-40 tiles per CTA, asynchronous TMA-store epilogue: repeated launches must be bit-identical
+    (catches staging-buffer reuse races) and equal to the reference."""
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    M = 32768
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    outs = []
+    for _ in range(4):
+        if mode == 0:
+            x = torch.ones((M, N), device="cuda")
+            outs.append(_gemm(lib, A, W, bias, 0, resid=x, out=x).clone())
+        else:
+            outs.append(_gemm(lib, A, W, bias, mode).clone())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    acc = A.float() @ W.float().t() + bias
+    ref = acc + 1.0 if mode == 0 else (torch.nn.functional.gelu(acc) if mode == 2 else acc)
+    err = (outs[0].float() - ref).abs().max().item()
+    assert err <= (2e-4 if mode == 0 else 2 ** -7) * ref.abs().max().item(), err
 
 
 def test_gemm_residual_inplace_and_broadcast(lib):
