@@ -35,7 +35,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
     ap.add_argument("--chunk", type=int, default=0, help="images per pipeline stage (0 = engine default)")
     ap.add_argument("--max-batch", type=int, default=0, help="images per super-chunk / CUDA graph (0 = default)")
+    ap.add_argument("--dec-chunk", type=int, default=0, help="images per decoder chain (0 = engine default 128)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-ar-kernel", action="store_true", help="AR loop as separate kernels instead of the persistent kernel")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM tile: 0 auto, 1 single CTA, 2 CTA pair")
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -213,8 +216,14 @@ def main():
         model.model.set_engine_option("max_batch", args.max_batch)
     if args.chunk:
         model.model.set_engine_option("chunk", args.chunk)
+    if args.dec_chunk:
+        model.model.set_engine_option("dec_chunk", args.dec_chunk)
     if args.no_graph:
         model.model.set_engine_option("use_graph", 0)
+    if args.no_pdl:
+        model.model.set_engine_option("pdl", 0)
+    if args.no_ar_kernel:
+        model.model.set_engine_option("ar_kernel", 0)
     if args.cta_group:
         model.model.set_engine_option("cta_group", args.cta_group)
     if args.block_n:
@@ -351,7 +360,7 @@ def main():
         "config": {"workload": "PARSeq-S 32x128 94-char max_len=25 bs=512/GPU AR + 1 refine (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, no collective)",
                    "l2": f"inputs rotate over {NROT} resident batches ({NROT * B * 49152 / 1e6:.0f} MB > 126 MB L2)",
-                   "chunk": args.chunk or (args.max_batch or 512), "max_batch": args.max_batch or 512, "cuda_graph": not args.no_graph},
+                   "chunk": args.chunk or (args.max_batch or 512), "max_batch": args.max_batch or 512, "dec_chunk": args.dec_chunk or 128, "cuda_graph": not args.no_graph},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1000 * e2e_s / args.steps},

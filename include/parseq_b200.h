@@ -100,13 +100,17 @@ int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* m
 
 /* Introspection used by bench.py / tests. */
 int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count of kernels launched */
-/* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per pipeline stage inside a
- * super-chunk: stage s decodes on its own stream while stage s+1 is being encoded), "use_graph" (0/1), "timing" (1: record a CUDA-event pair around every launch
+/* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per encoder pass inside a
+ * super-chunk), "dec_chunk" (images per decoder chain; the chains of a super-chunk run concurrently on their own
+ * streams), "use_graph" (0/1), "pdl" (programmatic dependent launch, 0/1), "timing" (1: record a CUDA-event pair around every launch
  * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests). */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of
  * category 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other. */
 int parseq_get_timing(parseq_engine* e, int category, double* ms, double* flops, int64_t* count);
+/* Debug: after a forward with option "ar_prof"=1, copies the [32 steps][16 slots] globaltimer (ns) stamps that block 0 of
+ * the persistent AR kernel recorded at its phase boundaries. */
+int parseq_get_ar_profile(parseq_engine* e, uint64_t* out512);
 const char* parseq_last_error(void);
 const char* parseq_version(void);
 

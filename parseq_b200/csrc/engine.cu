@@ -16,6 +16,7 @@
 #include "../../include/parseq_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "dec_ar.cuh"
 
 namespace {
 
@@ -82,6 +83,25 @@ uint16_t f32_to_bf16_rne(float f) {
 }
 
 int g_sm_count = 0;
+bool g_use_pdl = true;          // programmatic dependent launch on every kernel of the forward chain
+
+// cudaLaunchKernelEx wrapper: optional PDL attribute (the kernels call griddepcontrol.{launch_dependents,wait}).
+template <typename... KArgs, typename... Args>
+int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+  return PARSEQ_OK;
+}
+
 int g_block_n_override = 0;
 int g_cta_group_override = 0;   // 0 = auto, 1 / 2 = forced (tests)
 bool g_no_tma_epilogue = false; // tests: force the direct-store epilogue
@@ -103,13 +123,15 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   cfg.blockDim = dim3(pq::GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_use_pdl && CG == 1) ? 2 : 1;
   PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return PARSEQ_OK;
 }
@@ -121,7 +143,34 @@ int warm_gemm_cfg() {
                               pq::GemmCfg<BN, CG>::kSmemBytes) == cudaSuccess ? PARSEQ_OK
                                                                                 : fail(PARSEQ_ERR_CUDA, "cudaFuncSetAttribute(gemm)");
 }
+size_t head_smem_bytes(int C, int D) {
+  return ((static_cast<size_t>(C) * (D / 2 + 1) * 4 + 15) / 16) * 16 + static_cast<size_t>(pq::HEAD_ROWS) * D * 4 +
+         4 * pq::HEAD_ROWS * 128 * 4 + pq::HEAD_ROWS * 128 * 4;
+}
+int ln_head_argmax_launch(const float* y, const float* g, const float* b, float eps, const __nv_bfloat16* Wh, const float* bh,
+                          int M, int C, int D, float* logits, long long logits_ld, int* ids, int ids_ld, int nq, int dst_off,
+                          const int* forced, int forced_ld, cudaStream_t st) {
+  if (C > 128) return fail(PARSEQ_ERR_UNSUPPORTED, "head kernel covers at most 128 classes");
+  const dim3 grid((M + pq::HEAD_ROWS - 1) / pq::HEAD_ROWS), block(384);
+  const size_t sm = head_smem_bytes(C, D);
+  switch (D) {
+    case 192: return launch_k(pq::dec_ln_head_argmax_kernel<192>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
+                              logits_ld, ids, ids_ld, nq, dst_off, forced, forced_ld);
+    case 384: return launch_k(pq::dec_ln_head_argmax_kernel<384>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
+                              logits_ld, ids, ids_ld, nq, dst_off, forced, forced_ld);
+    case 768: return launch_k(pq::dec_ln_head_argmax_kernel<768>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
+                              logits_ld, ids, ids_ld, nq, dst_off, forced, forced_ld);
+    default: return fail(PARSEQ_ERR_UNSUPPORTED, "head kernel: embed_dim must be 192, 384 or 768");
+  }
+}
+
 int init_kernel_attributes() {
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<192>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   PQ_TRY((warm_gemm_cfg<64, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 1>()));
   PQ_TRY((warm_gemm_cfg<256, 1>()));
@@ -190,27 +239,23 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
 }
 
 int layernorm_launch(const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   const int rows_per_block = 8;
   const int grid = (M + rows_per_block - 1) / rows_per_block;
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   switch (D) {
-    case 192: pq::layernorm_kernel<192><<<grid, 256, 0, st>>>(x, g, b, eps, M, yb, y32); break;
-    case 384: pq::layernorm_kernel<384><<<grid, 256, 0, st>>>(x, g, b, eps, M, yb, y32); break;
-    case 768: pq::layernorm_kernel<768><<<grid, 256, 0, st>>>(x, g, b, eps, M, yb, y32); break;
+    case 192: return launch_k(pq::layernorm_kernel<192>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
+    case 384: return launch_k(pq::layernorm_kernel<384>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
+    case 768: return launch_k(pq::layernorm_kernel<768>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
     default: return fail(PARSEQ_ERR_UNSUPPORTED, "layernorm: embed_dim must be 192, 384 or 768");
   }
-  PQ_CUDA(cudaGetLastError());
-  return PARSEQ_OK;
 }
 
 int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
   if (T != pq::ATT_T || D != heads * pq::ATT_DH)
     return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernel covers T=128 tokens, head_dim=64");
-  pq::enc_attention_kernel<<<B * heads, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                      reinterpret_cast<__nv_bfloat16*>(out), D, heads);
-  PQ_CUDA(cudaGetLastError());
-  return PARSEQ_OK;
+  return launch_k(pq::enc_attention_kernel, dim3(B * heads), dim3(256), 0, st,
+                  reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), D, heads);
 }
 
 struct Slot {
@@ -244,8 +289,19 @@ struct parseq_engine {
   __nv_bfloat16 *a_pe = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr;
   float* x = nullptr;
   // per-stage decoder state: the decoder of stage s runs on its own stream while `main` encodes stage s+1
+  __nv_bfloat16 *mem = nullptr, *ckv = nullptr;   // [max_batch*T, D] encoder output, [max_batch*T, 2D] cross K/V
+  int dec_chunk = 128;              // images per decoder chain (each chain runs on its own stream)
+  // persistent AR-loop kernel state (whole super-chunk)
+  bool use_ar_kernel = true;
+  __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
+  float *ar_y = nullptr, *ar_qc = nullptr, *ar_part = nullptr;
+  int* ar_ids = nullptr;
+  unsigned int* ar_bar = nullptr;
+  unsigned long long* ar_prof = nullptr;   // [32][16] phase time stamps of the AR kernel (debug option "ar_prof")
+  bool ar_prof_on = false;
+  cudaEvent_t ev_enc = nullptr;
   struct Stage {
-    __nv_bfloat16 *mem = nullptr, *ckv = nullptr, *sa = nullptr, *yn = nullptr, *ca = nullptr, *hd = nullptr;
+    __nv_bfloat16 *sa = nullptr, *yn = nullptr, *ca = nullptr, *hd = nullptr;
     float *y = nullptr, *qc = nullptr;
     int *ids_ar = nullptr, *ids_ctx = nullptr;
     cudaStream_t stream = nullptr;
@@ -280,8 +336,9 @@ int dev_alloc(Tp** p, long long n) {
 }
 
 int alloc_workspace(parseq_engine* e) {
-  const long long R = static_cast<long long>(e->chunk) * e->T;
-  const long long Rd = static_cast<long long>(e->chunk) * e->L;
+  const long long R = static_cast<long long>(e->chunk) * e->T;          // encoder rows per chunk
+  const long long RB = static_cast<long long>(e->max_batch) * e->T;     // rows of a whole super-chunk
+  const long long Rd = static_cast<long long>(e->dec_chunk) * e->L;     // decoder rows per chain
   const int D = e->D;
   PQ_TRY(dev_alloc(&e->a_pe, R * e->Kp));
   PQ_TRY(dev_alloc(&e->x, R * D));
@@ -289,24 +346,34 @@ int alloc_workspace(parseq_engine* e) {
   PQ_TRY(dev_alloc(&e->qkv, R * 3 * D));
   PQ_TRY(dev_alloc(&e->att, R * D));
   PQ_TRY(dev_alloc(&e->hid, R * e->Me));
-  const int n_stages = (e->max_batch + e->chunk - 1) / e->chunk;
+  PQ_TRY(dev_alloc(&e->mem, RB * D));
+  PQ_TRY(dev_alloc(&e->ckv, RB * 2 * D));
+  PQ_TRY(dev_alloc(&e->ar_sa, 1ll * e->max_batch * D));
+  PQ_TRY(dev_alloc(&e->ar_ca, 1ll * e->max_batch * D));
+  PQ_TRY(dev_alloc(&e->ar_hd, 1ll * e->max_batch * e->Md));
+  PQ_TRY(dev_alloc(&e->ar_y, 1ll * e->max_batch * D));
+  PQ_TRY(dev_alloc(&e->ar_qc, 1ll * e->max_batch * D));
+  PQ_TRY(dev_alloc(&e->ar_part, 3ll * e->max_batch * D));
+  PQ_TRY(dev_alloc(&e->ar_ids, 1ll * e->max_batch * 32));
+  PQ_TRY(dev_alloc(&e->ar_bar, 64));
+  PQ_TRY(dev_alloc(&e->ar_prof, 32 * 16));
+  PQ_CUDA(cudaEventCreateWithFlags(&e->ev_enc, cudaEventDisableTiming));
+  const int n_stages = (e->max_batch + e->dec_chunk - 1) / e->dec_chunk;
   e->stages.resize(static_cast<size_t>(n_stages));
   for (auto& sg : e->stages) {
-    PQ_TRY(dev_alloc(&sg.mem, R * D));
-    PQ_TRY(dev_alloc(&sg.ckv, R * 2 * D));
     PQ_TRY(dev_alloc(&sg.sa, Rd * D));
     PQ_TRY(dev_alloc(&sg.yn, Rd * D));
     PQ_TRY(dev_alloc(&sg.ca, Rd * D));
     PQ_TRY(dev_alloc(&sg.hd, Rd * e->Md));
     PQ_TRY(dev_alloc(&sg.y, Rd * D));
     PQ_TRY(dev_alloc(&sg.qc, Rd * D));
-    PQ_TRY(dev_alloc(&sg.ids_ar, static_cast<long long>(e->chunk) * 32));
-    PQ_TRY(dev_alloc(&sg.ids_ctx, static_cast<long long>(e->chunk) * 32));
+    PQ_TRY(dev_alloc(&sg.ids_ar, static_cast<long long>(e->dec_chunk) * 32));
+    PQ_TRY(dev_alloc(&sg.ids_ctx, static_cast<long long>(e->dec_chunk) * 32));
     PQ_CUDA(cudaStreamCreateWithFlags(&sg.stream, cudaStreamNonBlocking));
     PQ_CUDA(cudaEventCreateWithFlags(&sg.ev_enc, cudaEventDisableTiming));
     PQ_CUDA(cudaEventCreateWithFlags(&sg.ev_done, cudaEventDisableTiming));
   }
-  const long long NB = static_cast<long long>(n_stages) * e->chunk;
+  const long long NB = e->max_batch;
   PQ_TRY(dev_alloc(&e->in_images, NB * 3 * e->cfg.img_h * e->cfg.img_w));
   PQ_TRY(dev_alloc(&e->out_logits, NB * e->L * e->C));
   PQ_TRY(dev_alloc(&e->out_ids, NB * e->L));
@@ -321,14 +388,18 @@ void drop_graphs(parseq_engine* e) {
 
 void free_workspace(parseq_engine* e) {
   drop_graphs(e);
-  void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->in_images, e->out_logits, e->out_ids, e->out_steps};
+  void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->mem, e->ckv, e->in_images, e->out_logits, e->out_ids,
+                  e->out_steps, e->ar_sa, e->ar_ca, e->ar_hd, e->ar_y, e->ar_qc, e->ar_part, e->ar_ids, e->ar_bar, e->ar_prof};
+  e->ar_part = nullptr; e->ar_prof = nullptr;
+  e->ar_sa = e->ar_ca = e->ar_hd = nullptr; e->ar_y = e->ar_qc = nullptr; e->ar_ids = nullptr; e->ar_bar = nullptr;
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  e->a_pe = e->xn = e->qkv = e->att = e->hid = nullptr;
+  if (e->ev_enc) { cudaEventDestroy(e->ev_enc); e->ev_enc = nullptr; }
+  e->a_pe = e->xn = e->qkv = e->att = e->hid = e->mem = e->ckv = nullptr;
   e->x = e->in_images = e->out_logits = nullptr;
   e->out_ids = e->out_steps = nullptr;
   for (auto& sg : e->stages) {
-    void* q[] = {sg.mem, sg.ckv, sg.sa, sg.yn, sg.ca, sg.hd, sg.y, sg.qc, sg.ids_ar, sg.ids_ctx};
+    void* q[] = {sg.sa, sg.yn, sg.ca, sg.hd, sg.y, sg.qc, sg.ids_ar, sg.ids_ctx};
     for (void* p : q)
       if (p) cudaFree(p);
     if (sg.stream) cudaStreamDestroy(sg.stream);
@@ -365,9 +436,9 @@ int gemm(parseq_engine* e, const void* A, long long lda, const void* W, long lon
   return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st);
 }
 int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float eps, int M, void* y, float* y32,
-              cudaStream_t st) {
+              cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   TimedScope ts(e, st, CAT_LN, 0.0);
-  return layernorm_launch(x, e->wf(prefix + ".weight"), e->wf(prefix + ".bias"), eps, M, e->D, y, y32, st);
+  return layernorm_launch(x, e->wf(prefix + ".weight"), e->wf(prefix + ".bias"), eps, M, e->D, y, y32, st, add, add_mod, xw);
 }
 
 // ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
@@ -379,9 +450,8 @@ int encode_chunk(parseq_engine* e, const float* images, int B, __nv_bfloat16* me
     TimedScope ts(e, st, CAT_MISC, 0.0);
     const long long total = static_cast<long long>(B) * e->gh * e->gw * 3 * e->cfg.patch_h;
     const int grid = static_cast<int>((total + 255) / 256);
-    pq::im2col_patch_kernel<<<grid, 256, 0, st>>>(images, e->a_pe, B, e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h,
-                                                  e->cfg.patch_w, e->gh, e->gw);
-    PQ_CUDA(cudaGetLastError());
+    PQ_TRY(launch_k(pq::im2col_patch_kernel, dim3(grid), dim3(256), 0, st, images, e->a_pe, B, e->cfg.img_h, e->cfg.img_w,
+                    e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
   }
   // x = patches * Wpe^T + bpe + pos_embed
   PQ_TRY(gemm(e, e->a_pe, e->Kp, e->w("encoder.patch_embed.proj.weight"), e->Kp,
@@ -410,8 +480,10 @@ int encode_chunk(parseq_engine* e, const float* images, int B, __nv_bfloat16* me
 
 // ---------------------------------------------------------------- one Decoder call (model.py:86-103, modules.py:55-125)
 // rows are (b, qi), qi in [0,nq); query position q0+qi; context ids[b, 0..nkeys-1].
-int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int B, int nq, int q0, int nkeys, int mode, const int* ids,
-                float* logits_out, long long logits_ld, cudaStream_t st) {
+// Tail: LayerNorm(decoder.norm) + head + (optionally) greedy argmax -> ids_dst[b*32 + dst_off + qi] in one kernel.
+int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16* ckv, int B, int nq, int q0, int nkeys,
+                int mode, const int* ids, float* logits_out, long long logits_ld, int* ids_dst, int dst_off,
+                const int* forced, int forced_ld, cudaStream_t st) {
   const int D = e->D, M = B * nq;
   const std::string Ly = "decoder.layers.0.";
   const float qscale = 1.0f / std::sqrt(static_cast<float>(e->dh_dec));
@@ -420,25 +492,20 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int B, int nq, int q
   e->cur_cat = CAT_DEC_GEMM;
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
-    pq::dec_self_attn_kernel<<<M, D, 0, st>>>(e->qs, e->kvtab, ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa);
-    PQ_CUDA(cudaGetLastError());
+    PQ_TRY(launch_k(pq::dec_self_attn2_kernel, dim3(B), dim3(D), 0, st, static_cast<const float*>(e->qs),
+                    static_cast<const __nv_bfloat16*>(e->kvtab), ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa));
   }
+  // y = pos_queries[q0+qi] + out_proj(sa): the GEMM stores out_proj(sa) with its TMA epilogue, the LayerNorm kernel
+  // adds the (broadcast) query residual, writes y back and emits norm1(y)
   const float* posq = e->wf("pos_queries") + static_cast<long long>(q0) * D;
   PQ_TRY(gemm(e, sg.sa, D, e->w(Ly + "self_attn.out_proj.weight"), D, e->wf(Ly + "self_attn.out_proj.bias"), M, D, D,
-              pq::EPI_F32, 1.0f, posq, D, nq, sg.y, D, st));
-  PQ_TRY(layernorm(e, sg.y, Ly + "norm1", 1e-5f, M, sg.yn, nullptr, st));
+              pq::EPI_F32, 1.0f, nullptr, 0, 0, sg.y, D, st));
+  PQ_TRY(layernorm(e, sg.y, Ly + "norm1", 1e-5f, M, sg.yn, nullptr, st, posq, nq, sg.y));
   PQ_TRY(gemm(e, sg.yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, sg.qc, D, st));
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
-    const int heads = e->cfg.dec_num_heads;
-    if (e->T <= 128) {
-      const size_t sm = static_cast<size_t>(heads) * (32 + 128) * sizeof(float);
-      pq::dec_cross_attn_kernel<128><<<M, D, sm, st>>>(sg.qc, sg.ckv, e->T, D, nq, sg.ca);
-    } else {
-      const size_t sm = static_cast<size_t>(heads) * (32 + 256) * sizeof(float);
-      pq::dec_cross_attn_kernel<256><<<M, D, sm, st>>>(sg.qc, sg.ckv, e->T, D, nq, sg.ca);
-    }
-    PQ_CUDA(cudaGetLastError());
+    PQ_TRY(launch_k(pq::dec_cross_attn3_kernel, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
+                    static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
   }
   PQ_TRY(gemm(e, sg.ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
               pq::EPI_F32, 1.0f, sg.y, D, 0, sg.y, D, st));
@@ -447,9 +514,12 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int B, int nq, int q
               1.0f, nullptr, 0, 0, sg.hd, e->Md, st));
   PQ_TRY(gemm(e, sg.hd, e->Md, e->w(Ly + "linear2.weight"), e->Md, e->wf(Ly + "linear2.bias"), M, D, e->Md, pq::EPI_F32,
               1.0f, sg.y, D, 0, sg.y, D, st));
-  PQ_TRY(layernorm(e, sg.y, "decoder.norm", 1e-5f, M, sg.yn, nullptr, st));
-  PQ_TRY(gemm(e, sg.yn, D, e->w("head.weight"), D, e->wf("head.bias"), M, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0,
-              logits_out, logits_ld, st));
+  {
+    TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * M * e->C * D);
+    PQ_TRY(ln_head_argmax_launch(sg.y, e->wf("decoder.norm.weight"), e->wf("decoder.norm.bias"), 1e-5f, e->wb("head.weight"),
+                                 e->wf("head.bias"), M, e->C, D, logits_out, logits_ld, ids_dst, 32, nq, dst_off, forced,
+                                 forced_ld, st));
+  }
   return PARSEQ_OK;
 }
 
@@ -458,86 +528,140 @@ int argmax_rows(parseq_engine* e, const float* logits, int L, int B, int nrows, 
   const int warps = B * nrows;
   if (warps <= 0) return PARSEQ_OK;
   TimedScope ts(e, st, CAT_MISC, 0.0);
-  pq::argmax_rows_kernel<<<(warps + 7) / 8, 256, 0, st>>>(logits, L, e->C, B, nrows, src0, ids, ids_ld, dst0, forced,
-                                                          forced_ld);
-  PQ_CUDA(cudaGetLastError());
-  return PARSEQ_OK;
+  return launch_k(pq::argmax_rows_kernel, dim3((warps + 7) / 8), dim3(256), 0, st, logits, L, e->C, B, nrows, src0, ids, ids_ld,
+                  dst0, forced, forced_ld);
 }
 
-// Decoder half of one pipeline stage (B <= chunk images whose memory is in sg.mem): cross K/V projection,
-// AR loop / NAR pass, cloze refinement, final argmax.  model.py:113-169.
-int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const parseq_forward_args* a, int b0, int B, int L,
-                 float* logits, int* ids_out, int* steps, cudaStream_t st) {
-  const int D = e->D, T = e->T, C = e->C;
+// Decoder chain of one group of B <= dec_chunk images (their cross K/V is at `ckv`): AR loop / NAR pass, cloze
+// refinement, final argmax.  model.py:113-169.
+int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16* ckv, const parseq_forward_args* a, int b0,
+                 int B, int L, float* logits, int* ids_out, int* steps, cudaStream_t st, bool ar_done) {
+  const int C = e->C;
   const int bos = e->V - 2, pad = e->V - 1;
   const bool testing = a->max_length < 0;
-  // cross-attention K/V of the image memory, once per image (the reference recomputes it in every decode call)
-  e->cur_cat = CAT_DEC_GEMM;
-  {
-    const std::string Ly = "decoder.layers.0.";
-    const __nv_bfloat16* Wkv = e->wb(Ly + "cross_attn.in_proj_weight") + static_cast<long long>(D) * D;
-    const float* bkv = e->wf(Ly + "cross_attn.in_proj_bias") + D;
-    PQ_TRY(gemm(e, sg.mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, sg.ckv, 2 * D, st));
-  }
   const long long LC = static_cast<long long>(L) * C;
-  if (a->decode_ar) {
-    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(sg.ids_ar, B, 32, bos, pad);
-    PQ_CUDA(cudaGetLastError());
+  if (a->decode_ar && ar_done) {
+    // the AR loop of the whole super-chunk already ran in the persistent kernel (ar_decode)
+  } else if (a->decode_ar) {
+    PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ar, B, 32, bos, pad));
     e->launches++;
     const int* forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
     for (int i = 0; i < L; ++i) {
-      PQ_TRY(decode_pass(e, sg, B, 1, i, i + 1, 0, sg.ids_ar, logits + static_cast<long long>(i) * C, LC, st));
-      if (i + 1 < L) PQ_TRY(argmax_rows(e, logits, L, B, 1, i, sg.ids_ar, 32, i + 1, forced, L, st));
+      // step i: context ids[:, :i+1], query position i; the fused tail writes ids[:, i+1] = argmax (model.py:142)
+      PQ_TRY(decode_pass(e, sg, ckv, B, 1, i, i + 1, 0, sg.ids_ar, logits + static_cast<long long>(i) * C, LC,
+                         (i + 1 < L) ? sg.ids_ar : nullptr, i + 1, forced, L, st));
     }
     if (testing && steps != nullptr) {
-      pq::ar_steps_kernel<<<1, 256, 0, st>>>(sg.ids_ar, 32, B, L, 0, steps);
-      PQ_CUDA(cudaGetLastError());
+      PQ_TRY(launch_k(pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(sg.ids_ar), 32, B, L, 0, steps));
       e->launches++;
     }
   } else {
-    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(sg.ids_ctx, B, 32, bos, pad);
-    PQ_CUDA(cudaGetLastError());
+    PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
     e->launches++;
-    PQ_TRY(decode_pass(e, sg, B, L, 0, 1, 0, sg.ids_ctx, logits, C, st));
+    PQ_TRY(decode_pass(e, sg, ckv, B, L, 0, 1, 0, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
   }
   for (int it = 0; it < a->refine_iters; ++it) {
-    pq::fill_ids_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(sg.ids_ctx, B, 32, bos, pad);
-    PQ_CUDA(cudaGetLastError());
+    PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
     e->launches++;
     const int* forced = a->forced_refine
                             ? a->forced_refine + (static_cast<long long>(it) * a->batch + b0) * L
                             : nullptr;
     // ctx = [BOS, argmax(logits[:, :L-1])]  (model.py:161)
     PQ_TRY(argmax_rows(e, logits, L, B, L - 1, 0, sg.ids_ctx, 32, 1, forced, L, st));
-    PQ_TRY(decode_pass(e, sg, B, L, 0, L, 1, sg.ids_ctx, logits, C, st));
+    PQ_TRY(decode_pass(e, sg, ckv, B, L, 0, L, 1, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
   }
   if (ids_out != nullptr) PQ_TRY(argmax_rows(e, logits, L, B, L, 0, ids_out, L, 0, nullptr, 0, st));
   return PARSEQ_OK;
 }
 
-// One super-chunk (B <= max_batch images) as a software pipeline over stages of `chunk` images:
-// `main` encodes stage s, then stage s's decoder (a latency-bound chain of small kernels) runs on the stage's
-// own stream while `main` already encodes stage s+1.  Fork/join with events (capturable into a CUDA graph).
+// The whole AR loop (model.py:119-147) of B images in one persistent launch (csrc/dec_ar.cuh).
+int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, float* logits, int* steps, cudaStream_t st) {
+  const int D = e->D;
+  const std::string Ly = "decoder.layers.0.";
+  const bool testing = a->max_length < 0;
+  PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, e->ar_ids, B, 32, e->V - 2, e->V - 1));
+  e->launches++;
+  PQ_CUDA(cudaMemsetAsync(e->ar_bar, 0, 64, st));
+  pq::DecArParams p;
+  p.B = B; p.L = L; p.Md = e->Md; p.V = e->V; p.C = e->C; p.T = e->T; p.heads = e->cfg.dec_num_heads;
+  p.qscale = 1.0f / std::sqrt(static_cast<float>(e->dh_dec));
+  p.qs = e->qs; p.kvtab = e->kvtab; p.posq = e->wf("pos_queries");
+  p.Wo_s = e->wb(Ly + "self_attn.out_proj.weight"); p.bo_s = e->wf(Ly + "self_attn.out_proj.bias");
+  p.Wq_c = e->wb(Ly + "cross_attn.in_proj_weight"); p.bq_c = e->wf(Ly + "cross_attn.in_proj_bias");
+  p.Wo_c = e->wb(Ly + "cross_attn.out_proj.weight"); p.bo_c = e->wf(Ly + "cross_attn.out_proj.bias");
+  p.W1 = e->wb(Ly + "linear1.weight"); p.b1 = e->wf(Ly + "linear1.bias");
+  p.W2 = e->wb(Ly + "linear2.weight"); p.b2 = e->wf(Ly + "linear2.bias");
+  p.Wh = e->wb("head.weight"); p.bh = e->wf("head.bias");
+  p.g1 = e->wf(Ly + "norm1.weight"); p.be1 = e->wf(Ly + "norm1.bias");
+  p.g2 = e->wf(Ly + "norm2.weight"); p.be2 = e->wf(Ly + "norm2.bias");
+  p.g3 = e->wf("decoder.norm.weight"); p.be3 = e->wf("decoder.norm.bias");
+  p.ckv = e->ckv; p.ids = e->ar_ids; p.ids_ld = 32;
+  p.sa = e->ar_sa; p.ca = e->ar_ca; p.hd = e->ar_hd; p.y = e->ar_y; p.qc = e->ar_qc; p.part = e->ar_part;
+  p.logits = logits;
+  p.forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
+  p.forced_ld = L;
+  p.bar = e->ar_bar;
+  p.prof = e->ar_prof_on ? e->ar_prof : nullptr;
+  {
+    // per image and step: 3 D^2 (self out, cross q, cross out) + 2 D Md (MLP) + C D (head) + attention dots
+    const double macs = static_cast<double>(B) * L * (3.0 * D * D + 2.0 * D * e->Md + 1.0 * e->C * D + 2.0 * e->T * D);
+    TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * macs);
+    const dim3 grid(static_cast<unsigned>(g_sm_count)), block(pq::DEC_THREADS);
+    switch (D) {
+      case 192: PQ_TRY(launch_k(pq::dec_ar_kernel<192>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p)); break;
+      case 384: PQ_TRY(launch_k(pq::dec_ar_kernel<384>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p)); break;
+      case 768: PQ_TRY(launch_k(pq::dec_ar_kernel<768>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p)); break;
+      default: return fail(PARSEQ_ERR_UNSUPPORTED, "dec_ar: embed_dim must be 192, 384 or 768");
+    }
+  }
+  if (testing && steps != nullptr) {
+    PQ_TRY(launch_k(pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(e->ar_ids), 32, B, L, 0, steps));
+    e->launches++;
+  }
+  return PARSEQ_OK;
+}
+
+// One super-chunk (B <= max_batch images): `main` encodes everything (in `chunk`-image pieces) and projects the cross
+// K/V of the whole super-chunk; then the decoder - a latency-bound chain of small kernels - runs as ceil(B/dec_chunk)
+// independent chains on their own streams, concurrently (event fork/join, capturable into a CUDA graph).
 int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const float* images,
                   float* logits, int* ids_out, int* steps) {
   const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
-  const int n = (B + e->chunk - 1) / e->chunk;
+  const int D = e->D, T = e->T;
+  for (int o = 0; o < B; o += e->chunk) {
+    const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
+    PQ_TRY(encode_chunk(e, images + o * img_sz, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
+  }
+  // cross-attention K/V of the image memory, once per image (the reference recomputes it in every decode call)
+  e->cur_cat = CAT_DEC_GEMM;
+  {
+    const std::string Ly = "decoder.layers.0.";
+    const __nv_bfloat16* Wkv = e->wb(Ly + "cross_attn.in_proj_weight") + static_cast<long long>(D) * D;
+    const float* bkv = e->wf(Ly + "cross_attn.in_proj_bias") + D;
+    PQ_TRY(gemm(e, e->mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, e->ckv, 2 * D, e->main));
+  }
+  const bool ar_done = a->decode_ar && e->use_ar_kernel;
+  if (ar_done) {
+    PQ_TRY(ar_decode(e, a, b0, B, L, logits, steps, e->main));
+    if (a->refine_iters == 0) {      // nothing left for the chains but the final argmax
+      if (ids_out != nullptr) PQ_TRY(argmax_rows(e, logits, L, B, L, 0, ids_out, L, 0, nullptr, 0, e->main));
+      return PARSEQ_OK;
+    }
+  }
+  const int n = (B + e->dec_chunk - 1) / e->dec_chunk;
+  const bool fork = (n > 1) && !e->timing;      // timing mode: everything on `main` (isolated kernel times)
+  if (fork) PQ_CUDA(cudaEventRecord(e->ev_enc, e->main));
   for (int s = 0; s < n; ++s) {
     parseq_engine::Stage& sg = e->stages[static_cast<size_t>(s)];
-    const int o = s * e->chunk;
-    const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
-    PQ_TRY(encode_chunk(e, images + o * img_sz, Bs, sg.mem, nullptr, e->main));
-    const bool fork = (n > 1) && !e->timing;   // timing mode: everything on `main` (isolated kernel times)
+    const int o = s * e->dec_chunk;
+    const int Bs = (B - o < e->dec_chunk) ? (B - o) : e->dec_chunk;
     cudaStream_t ds = fork ? sg.stream : e->main;
-    if (fork) {
-      PQ_CUDA(cudaEventRecord(sg.ev_enc, e->main));
-      PQ_CUDA(cudaStreamWaitEvent(ds, sg.ev_enc, 0));
-    }
-    PQ_TRY(decode_stage(e, sg, a, b0 + o, Bs, L, logits + 1ll * o * L * e->C, ids_out ? ids_out + 1ll * o * L : nullptr,
-                        steps, ds));
+    if (fork) PQ_CUDA(cudaStreamWaitEvent(ds, e->ev_enc, 0));
+    PQ_TRY(decode_stage(e, sg, e->ckv + 1ll * o * T * 2 * D, a, b0 + o, Bs, L, logits + 1ll * o * L * e->C,
+                        ids_out ? ids_out + 1ll * o * L : nullptr, steps, ds, ar_done));
     if (fork) PQ_CUDA(cudaEventRecord(sg.ev_done, ds));
   }
-  if (n > 1 && !e->timing)
+  if (fork)
     for (int s = 0; s < n; ++s) PQ_CUDA(cudaStreamWaitEvent(e->main, e->stages[static_cast<size_t>(s)].ev_done, 0));
   return PARSEQ_OK;
 }
@@ -589,8 +713,7 @@ int forward_impl(parseq_engine* e, const parseq_forward_args* a, const float* im
   // user stream -> main
   PQ_CUDA(cudaEventRecord(e->ev_in, user));
   PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
-  pq::set_int_kernel<<<1, 32, 0, e->main>>>(e->out_steps, (testing && a->decode_ar) ? 0 : L);
-  PQ_CUDA(cudaGetLastError());
+  PQ_TRY(launch_k(pq::set_int_kernel, dim3(1), dim3(32), 0, e->main, e->out_steps, (testing && a->decode_ar) ? 0 : L));
   e->launches++;
   for (int b0 = 0; b0 < a->batch; b0 += e->max_batch) {
     const int Bc = (a->batch - b0 < e->max_batch) ? (a->batch - b0) : e->max_batch;
@@ -664,6 +787,7 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   // One pipeline stage per super-chunk by default: measured on B200 the decoder chain is latency-bound and the
   // encoder GEMMs occupy every SM, so splitting into stages only shrinks the GEMMs ("chunk" option re-enables it).
   e->chunk = e->max_batch;
+  e->dec_chunk = e->max_batch < 128 ? e->max_batch : 128;
   if (e->T != 128) {
     delete e;
     return fail(PARSEQ_ERR_UNSUPPORTED, "this build covers 128-token images (32x128 / patch 4x8)");
@@ -854,7 +978,7 @@ int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* m
   const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
   for (int b0 = 0; b0 < batch; b0 += e->chunk) {
     const int B = (batch - b0 < e->chunk) ? (batch - b0) : e->chunk;
-    PQ_TRY(encode_chunk(e, images + b0 * img_sz, B, e->stages[0].mem, memory + 1ll * b0 * e->T * e->D, e->main));
+    PQ_TRY(encode_chunk(e, images + b0 * img_sz, B, e->mem, memory + 1ll * b0 * e->T * e->D, e->main));
   }
   PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
   PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
@@ -872,6 +996,7 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     g_block_n_override = static_cast<int>(value);
     return PARSEQ_OK;
   }
+  if (n == "pdl") { g_use_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
   if (n == "cta_group") {
     if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "cta_group: 0 (auto) / 1 / 2");
@@ -886,17 +1011,28 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     return PARSEQ_OK;
   }
   if (n == "use_graph") { e->use_graph = value != 0; return PARSEQ_OK; }
-  if (n == "chunk" || n == "max_batch") {
-    if (value <= 0 || value > 8192) return fail(PARSEQ_ERR_INVALID_ARG, "chunk / max_batch out of range");
+  if (n == "ar_prof") { e->ar_prof_on = value != 0; drop_graphs(e); return PARSEQ_OK; }
+  if (n == "ar_kernel") { e->use_ar_kernel = value != 0; drop_graphs(e); return PARSEQ_OK; }
+  if (n == "chunk" || n == "max_batch" || n == "dec_chunk") {
+    if (value <= 0 || value > 8192) return fail(PARSEQ_ERR_INVALID_ARG, "chunk / max_batch / dec_chunk out of range");
     PQ_CUDA(cudaSetDevice(e->cfg.device));
     PQ_CUDA(cudaDeviceSynchronize());
     free_workspace(e);
-    if (n == "chunk") e->chunk = static_cast<int>(value); else e->max_batch = static_cast<int>(value);
+    if (n == "chunk") e->chunk = static_cast<int>(value);
+    else if (n == "dec_chunk") e->dec_chunk = static_cast<int>(value);
+    else { e->max_batch = static_cast<int>(value); e->chunk = e->max_batch; }
     if (e->chunk > e->max_batch) e->chunk = e->max_batch;
-    if ((e->max_batch + e->chunk - 1) / e->chunk > 64) return fail(PARSEQ_ERR_INVALID_ARG, "too many pipeline stages");
+    if (e->dec_chunk > e->max_batch) e->dec_chunk = e->max_batch;
+    if ((e->max_batch + e->dec_chunk - 1) / e->dec_chunk > 64) return fail(PARSEQ_ERR_INVALID_ARG, "too many decoder chains");
     return alloc_workspace(e);
   }
   return fail(PARSEQ_ERR_INVALID_ARG, "unknown option: " + n);
+}
+
+int parseq_get_ar_profile(parseq_engine* e, uint64_t* out512) {
+  if (e == nullptr || out512 == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  PQ_CUDA(cudaMemcpy(out512, e->ar_prof, 32 * 16 * 8, cudaMemcpyDeviceToHost));
+  return PARSEQ_OK;
 }
 
 int parseq_get_timing(parseq_engine* e, int category, double* ms, double* flops, int64_t* count) {

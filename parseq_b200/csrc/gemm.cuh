@@ -251,6 +251,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;    // tiles of (128*CG) x BLOCK_N
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
+  grid_dep_launch();                       // PDL: the next kernel may start its own prologue
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -273,6 +274,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_wait();                         // PDL: inputs of this GEMM are complete and visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================

@@ -12,6 +12,8 @@ namespace pq {
 // One thread per (token, ch, dy): reads pw contiguous floats, writes pw contiguous bf16.
 __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
                                     int W, int ph, int pw, int gh, int gw) {
+  grid_dep_launch();
+  grid_dep_wait();
   const long long total = static_cast<long long>(B) * gh * gw * 3 * ph;
   const int Kp = 3 * ph * pw;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -32,10 +34,16 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (biased variance, two-pass in registers), one warp per row.
 // y_bf16 = bf16(LN(x)); optional fp32 copy (encoder output `memory`).
+// Optional pre-add: x_row += add[(row % add_mod)] (broadcast table, e.g. pos_queries) and the sum is written back
+// to xw (the residual stream) before normalising - lets the producing GEMM use its plain TMA-store epilogue.
 template <int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int M,
-                                                        __nv_bfloat16* __restrict__ y, float* __restrict__ y32) {
+                                                        __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                                                        const float* __restrict__ add, int add_mod,
+                                                        float* __restrict__ xw) {
+  grid_dep_launch();
+  grid_dep_wait();
   static_assert(D % 64 == 0, "D must be a multiple of 64");
   constexpr int NV = D / 64;  // float2 per lane
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -45,10 +53,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float2 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = xr[i * 32 + lane];
-    s += v[i].x + v[i].y;
+  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+  if (add != nullptr) {
+    const float2* ar = reinterpret_cast<const float2*>(add + static_cast<long long>(row % add_mod) * D);
+    float2* wr = reinterpret_cast<float2*>(xw + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float2 a = __ldg(ar + i * 32 + lane);
+      v[i].x += a.x;
+      v[i].y += a.y;
+      wr[i * 32 + lane] = v[i];
+    }
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s * (1.0f / D);
@@ -84,8 +102,10 @@ constexpr int ATT_DH = 64;
 __device__ __forceinline__ uint32_t att_swz(int r, int c) {  // element offset of (row r, col c), c%8==0 chunks
   return static_cast<uint32_t>(r * ATT_DH + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7)));
 }
-__global__ void __launch_bounds__(256) enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(256, 2) enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ out, int D, int heads) {
+  grid_dep_launch();
+  grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[ATT_T * ATT_DH];
   __shared__ __align__(128) __nv_bfloat16 sK[ATT_T * ATT_DH];
   __shared__ __align__(128) __nv_bfloat16 sV[ATT_T * ATT_DH];
@@ -227,6 +247,8 @@ __global__ void build_ctx_rows_kernel(const float* __restrict__ emb, const float
 __global__ void dec_self_attn_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
                                      const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
                                      int mode, int eos_id, __nv_bfloat16* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int b = blockIdx.x / nq, qi = blockIdx.x % nq;
   const int qpos = q0 + qi;
   const int c = threadIdx.x;             // channel; blockDim.x == D
@@ -343,6 +365,8 @@ __global__ void dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bf
 __global__ void argmax_rows_kernel(const float* __restrict__ logits, int L, int C, int B, int nrows_per_b, int src_pos0,
                                    int* __restrict__ ids, int ids_ld, int dst_pos0, const int* __restrict__ forced,
                                    int forced_ld) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= B * nrows_per_b) return;
   const int lane = threadIdx.x & 31;
@@ -368,6 +392,8 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, int L, int 
 }
 
 __global__ void fill_ids_kernel(int* __restrict__ ids, int B, int ld, int bos, int pad) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * ld) ids[i] = ((i % ld) == 0) ? bos : pad;
 }
@@ -379,6 +405,8 @@ __global__ void copy_ids_kernel(const int* __restrict__ src, int src_ld, int* __
 // S = number of AR steps the reference returns under its batch-wide early exit (model.py:144):
 // smallest j>=1 such that every row has an EOS among ids[b,1..j]  == max_b first_eos_pos(b); L if any row has none.
 __global__ void ar_steps_kernel(const int* __restrict__ ids, int ids_ld, int B, int L, int eos_id, int* __restrict__ steps) {
+  grid_dep_launch();
+  grid_dep_wait();
   int worst = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     int first = L;
@@ -388,6 +416,282 @@ __global__ void ar_steps_kernel(const int* __restrict__ ids, int ids_ld, int B, 
   }
   atomicMax(steps, worst);
 }
-__global__ void set_int_kernel(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+__global__ void set_int_kernel(int* p, int v) {
+  grid_dep_launch();
+  grid_dep_wait(); if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+
+// ---------------------------------------------------------------------------------------------
+// Decoder self-attention, one CTA per image, one warp per head (head dim 32), ALL nq queries of the pass:
+// the context K rows (lane = key, <= 32 keys) and V columns (lane = channel) of the head are gathered once from the
+// (position, token) table into registers, then every query costs ~130 warp instructions.  Same semantics as
+// dec_self_attn_kernel (kept for reference / tests).
+__global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
+                                      const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
+                                      int mode, int eos_id, __nv_bfloat16* __restrict__ out) {
+  __shared__ int s_ids[32];
+  __shared__ int s_first_eos;
+  grid_dep_launch();
+  grid_dep_wait();
+  const int b = blockIdx.x;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const int id = (threadIdx.x < nkeys) ? ids[static_cast<long long>(b) * ids_ld + threadIdx.x] : -1;
+    s_ids[threadIdx.x] = id;
+    const unsigned m = __ballot_sync(0xffffffffu, id == eos_id);
+    if (threadIdx.x == 0) s_first_eos = (m != 0u) ? (__ffs(m) - 1) : (1 << 30);
+  }
+  __syncthreads();
+  const int first_eos = s_first_eos;
+  float kreg[32], vreg[32];
+  if (lane < nkeys) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kvtab + (static_cast<long long>(lane) * V + s_ids[lane]) * 2 * D + h * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = __ldg(kr + j);
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(p2[e]);
+        kreg[j * 8 + e * 2] = f.x;
+        kreg[j * 8 + e * 2 + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) kreg[j] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    vreg[k] = (k < nkeys) ? __bfloat162float(kvtab[(static_cast<long long>(k) * V + s_ids[k]) * 2 * D + D + h * 32 + lane]) : 0.f;
+  for (int qi = 0; qi < nq; ++qi) {
+    const int qpos = q0 + qi;
+    const float qv = __ldg(Qs + static_cast<long long>(qpos) * D + h * 32 + lane);   // lane j holds q_j
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s = fmaf(__shfl_sync(0xffffffffu, qv, j), kreg[j], s);
+    const bool masked = (lane >= nkeys) || ((mode == 1) && (lane == qpos + 1 || lane >= first_eos));
+    if (masked) s = -INFINITY;
+    float mx = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = masked ? 0.f : expf(s - mx);
+    float sum = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float pme = e / sum;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, pme, k), vreg[k], acc);
+    out[(static_cast<long long>(b) * nq + qi) * D + h * 32 + lane] = __float2bfloat16_rn(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder cross-attention: one CTA per (image, head), 4 warps.  The head's K (padded pitch, lane = key reads are
+// conflict-free) and V tiles are staged once in shared memory, so the per-image K/V cache is read once per decode
+// pass; the nq queries are distributed over the warps and each query is handled entirely inside one warp (scores
+// for 4 keys per lane, shuffle softmax, lane = channel for P.V): no block-level synchronisation after the load.
+// q fp32 [B*nq, D] pre-scaled by 1/sqrt(32); kv bf16 [B, T, 2D]; out bf16 [B*nq, D].  T <= 128, head dim 32.
+__global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __restrict__ q,
+                                                              const __nv_bfloat16* __restrict__ kv, int T, int D, int heads,
+                                                              int nq, __nv_bfloat16* __restrict__ out) {
+  __shared__ uint32_t sK[128 * 17];                       // bf16x2 words, pitch 17 (odd)
+  __shared__ __align__(16) __nv_bfloat16 sV[128 * 32];
+  grid_dep_launch();
+  grid_dep_wait();
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const __nv_bfloat16* kvb = kv + static_cast<long long>(b) * T * 2 * D;
+  {
+    uint4* vd = reinterpret_cast<uint4*>(sV + t * 32);
+    if (t < T) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + h * 32);
+      const uint4* vr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + D + h * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = __ldg(kr + j);
+        sK[t * 17 + j * 4 + 0] = u.x; sK[t * 17 + j * 4 + 1] = u.y;
+        sK[t * 17 + j * 4 + 2] = u.z; sK[t * 17 + j * 4 + 3] = u.w;
+        vd[j] = __ldg(vr + j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sK[t * 17 + j] = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vd[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  __syncthreads();
+  for (int qi = warp; qi < nq; qi += 4) {
+    const long long row = static_cast<long long>(b) * nq + qi;
+    const float qv = q[row * D + h * 32 + lane];          // lane j holds q_j
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const float qa = __shfl_sync(0xffffffffu, qv, 2 * w), qb = __shfl_sync(0xffffffffu, qv, 2 * w + 1);
+      const uint32_t k0 = sK[lane * 17 + w], k1 = sK[(32 + lane) * 17 + w], k2 = sK[(64 + lane) * 17 + w],
+                     k3 = sK[(96 + lane) * 17 + w];
+      s0 = fmaf(qb, __uint_as_float(k0 & 0xffff0000u), fmaf(qa, __uint_as_float(k0 << 16), s0));
+      s1 = fmaf(qb, __uint_as_float(k1 & 0xffff0000u), fmaf(qa, __uint_as_float(k1 << 16), s1));
+      s2 = fmaf(qb, __uint_as_float(k2 & 0xffff0000u), fmaf(qa, __uint_as_float(k2 << 16), s2));
+      s3 = fmaf(qb, __uint_as_float(k3 & 0xffff0000u), fmaf(qa, __uint_as_float(k3 << 16), s3));
+    }
+    if (lane >= T) s0 = -INFINITY;
+    if (32 + lane >= T) s1 = -INFINITY;
+    if (64 + lane >= T) s2 = -INFINITY;
+    if (96 + lane >= T) s3 = -INFINITY;
+    float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e0 = expf(s0 - mx), e1 = expf(s1 - mx), e2 = expf(s2 - mx), e3 = expf(s3 - mx);
+    float sum = (e0 + e1) + (e2 + e3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      acc = fmaf(__shfl_sync(0xffffffffu, e0, k), __bfloat162float(sV[k * 32 + lane]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e1, k), __bfloat162float(sV[(32 + k) * 32 + lane]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e2, k), __bfloat162float(sV[(64 + k) * 32 + lane]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e3, k), __bfloat162float(sV[(96 + k) * 32 + lane]), acc);
+    }
+    out[row * D + h * 32 + lane] = __float2bfloat16_rn(acc * (1.0f / sum));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused tail of a decoder pass: out = LayerNorm(y; decoder.norm) -> logits = head(out) -> greedy argmax
+// (modules.py:124 `Decoder.norm`, model.py:138 `self.head`, model.py:142 argmax).  4 rows per CTA; the head weight
+// (C x D bf16, 73 KB for 95 x 384) is staged in shared memory with an odd word pitch (lane = class reads are
+// conflict-free); each warp computes a (32 classes x 4 rows) partial over a quarter of K; the normalised rows are
+// rounded to bf16 exactly like a tensor-core A operand.
+// logits fp32: row r -> logits[r * logits_ld .. + C); ids (optional): row r = (b, qi) -> ids[b*ids_ld + dst_off + qi].
+constexpr int HEAD_ROWS = 4;
+template <int D>
+__global__ void __launch_bounds__(384) dec_ln_head_argmax_kernel(
+    const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    const __nv_bfloat16* __restrict__ Wh, const float* __restrict__ bh, int M, int C, float* __restrict__ logits,
+    long long logits_ld, int* __restrict__ ids, int ids_ld, int nq, int dst_off, const int* __restrict__ forced,
+    int forced_ld) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  constexpr int WP = D / 2 + 1;                         // weight row pitch in 32-bit words (odd -> conflict-free)
+  uint32_t* sW = reinterpret_cast<uint32_t*>(head_smem);            // [C][WP] bf16x2
+  float* sy = reinterpret_cast<float*>(head_smem + ((static_cast<size_t>(C) * WP * 4 + 15) / 16) * 16);   // [4][D]
+  float* spart = sy + HEAD_ROWS * D;                                // [4 k-quarters][4 rows][128]
+  float* sl = spart + 4 * HEAD_ROWS * 128;                          // [4][128] logits
+  grid_dep_launch();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
+  // (weights do not depend on the previous kernel: stage them before the dependency wait)
+  const uint32_t* Wg = reinterpret_cast<const uint32_t*>(Wh);
+  for (int i = tid; i < C * (D / 2); i += blockDim.x) {
+    const int c = i / (D / 2), k = i % (D / 2);
+    sW[c * WP + k] = __ldg(Wg + i);
+  }
+  grid_dep_wait();
+  const int row0 = blockIdx.x * HEAD_ROWS;
+  // ---- LayerNorm of up to 4 rows (warp per row), rounded to bf16 ----
+  constexpr int NV = D / 64;
+  if (warp < HEAD_ROWS) {
+    const int r = warp;
+    const int row = row0 + r;
+    float2 v[NV];
+    if (row < M) {
+      const float2* xr = reinterpret_cast<const float2*>(y + static_cast<long long>(row) * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = make_float2(0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float qv = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean;
+      qv += a * a + b2 * b2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
+    const float rstd = 1.0f / sqrtf(qv * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + i * 32 + lane);
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(beta) + i * 32 + lane);
+      const float o0 = (v[i].x - mean) * rstd * g.x + bb.x;
+      const float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+      reinterpret_cast<float2*>(sy + r * D)[i * 32 + lane] =
+          make_float2(__bfloat162float(__float2bfloat16_rn(o0)), __bfloat162float(__float2bfloat16_rn(o1)));
+    }
+  }
+  __syncthreads();
+  // ---- head partials: unit = (class pass of 32, quarter of K); lane = class; 4 rows at once ----
+  const int passes = (C + 31) / 32;
+  constexpr int KQ = D / 8;                               // words per K quarter
+  for (int u = warp; u < passes * 4; u += nwarps) {
+    const int c = (u >> 2) * 32 + lane;
+    const int kq = u & 3;
+    const int cc = (c < C) ? c : (C - 1);
+    const uint32_t* wr = sW + cc * WP + kq * KQ;
+    const float* y0 = sy + kq * KQ * 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < KQ; ++k) {
+      const uint32_t w2 = wr[k];
+      const float wx = __uint_as_float(w2 << 16), wy = __uint_as_float(w2 & 0xffff0000u);
+      const float2 p0 = *reinterpret_cast<const float2*>(y0 + 2 * k);
+      const float2 p1 = *reinterpret_cast<const float2*>(y0 + D + 2 * k);
+      const float2 p2 = *reinterpret_cast<const float2*>(y0 + 2 * D + 2 * k);
+      const float2 p3 = *reinterpret_cast<const float2*>(y0 + 3 * D + 2 * k);
+      a0 = fmaf(wy, p0.y, fmaf(wx, p0.x, a0));
+      a1 = fmaf(wy, p1.y, fmaf(wx, p1.x, a1));
+      a2 = fmaf(wy, p2.y, fmaf(wx, p2.x, a2));
+      a3 = fmaf(wy, p3.y, fmaf(wx, p3.x, a3));
+    }
+    float* sp = spart + (kq * HEAD_ROWS) * 128 + (c & 127);
+    sp[0] = a0; sp[128] = a1; sp[256] = a2; sp[384] = a3;
+  }
+  __syncthreads();
+  for (int i = tid; i < HEAD_ROWS * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    const float l = ((spart[(0 * HEAD_ROWS + r) * 128 + c] + spart[(1 * HEAD_ROWS + r) * 128 + c]) +
+                     (spart[(2 * HEAD_ROWS + r) * 128 + c] + spart[(3 * HEAD_ROWS + r) * 128 + c])) + __ldg(bh + c);
+    sl[r * 128 + c] = l;
+    const int row = row0 + r;
+    if (row < M) logits[static_cast<long long>(row) * logits_ld + c] = l;
+  }
+  if (ids == nullptr) return;
+  __syncthreads();
+  // ---- greedy argmax (first maximum wins), warp per row ----
+  if (warp < HEAD_ROWS) {
+    const int r = warp;
+    const int row = row0 + r;
+    if (row < M) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int j = lane; j < C; j += 32) {
+        const float v = sl[r * 128 + j];
+        if (v > best) { best = v; bi = j; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        const int b = row / nq, qi = row % nq;
+        int v = bi;
+        if (forced != nullptr) v = forced[static_cast<long long>(b) * forced_ld + dst_off + qi];
+        ids[static_cast<long long>(b) * ids_ld + dst_off + qi] = v;
+      }
+    }
+  }
+}
 
 }  // namespace pq

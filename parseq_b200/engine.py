@@ -26,7 +26,7 @@ class ForwardArgsC(C.Structure):
 EXPORTS = [
     "parseq_create", "parseq_destroy", "parseq_set_weight", "parseq_num_weights", "parseq_weight_key",
     "parseq_finalize", "parseq_forward", "parseq_forward_host", "parseq_encode", "parseq_kernel_launches",
-    "parseq_set_option", "parseq_get_timing", "parseq_last_error", "parseq_version", "parseq_gemm_bf16", "parseq_layernorm_bf16",
+    "parseq_set_option", "parseq_get_timing", "parseq_get_ar_profile", "parseq_last_error", "parseq_version", "parseq_gemm_bf16", "parseq_layernorm_bf16",
     "parseq_enc_attention",
 ]
 
@@ -139,6 +139,12 @@ class Engine:
             check(self.lib, self.lib.parseq_get_timing(self.handle, i, C.byref(ms), C.byref(fl), C.byref(n)))
             out[name] = dict(ms=ms.value, flops=fl.value, launches=n.value)
         return out
+
+    def get_ar_profile(self):
+        buf = (C.c_uint64 * 512)()
+        self.lib.parseq_get_ar_profile.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        check(self.lib, self.lib.parseq_get_ar_profile(self.handle, buf))
+        return [[buf[s * 16 + k] for k in range(16)] for s in range(32)]
 
     @property
     def launches(self) -> int:

@@ -1,0 +1,19 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from parseq_b200.config import make_config
+from parseq_b200.factory import create_model
+from parseq_b200.weights import init_state_dict, synth_images
+cfg = make_config("parseq"); sd = init_state_dict(cfg, 0)
+m = create_model("parseq", decode_ar=True, refine_iters=0); m.model.load_state_dict(sd)
+m.model.set_engine_option("ar_prof", 1)
+m = m.eval().to("cuda")
+x = synth_images(cfg, 512, 1).cuda()
+with torch.inference_mode():
+    for _ in range(3): m(x, 25)
+torch.cuda.synchronize()
+prof = m.model.engine().get_ar_profile()
+names = ["P1 self", "bar", "P2 oproj", "bar", "P3 ln+q", "bar", "P4 cross", "bar", "P5 oproj", "bar", "P6 ln+l1", "bar", "P7 l2", "bar", "P8 head"]
+for step in (1, 12, 25):
+    t = prof[step]
+    print(f"step {step}: " + "  ".join(f"{names[k]}={(t[k+1]-t[k])/1000:.1f}" for k in range(15)), f" | total {(t[15]-t[0])/1000:.1f} us")
