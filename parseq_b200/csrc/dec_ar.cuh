@@ -92,20 +92,23 @@ struct DecSmem {   // byte offsets into dynamic shared memory
 // through a 3-stage cp.async ring (each stage costs one L2 round trip, so depth matters more than width here).
 constexpr int DEC_STAGES = 4;
 constexpr int DEC_MAX_BN = 128;
-template <int D, int NT, bool LN_A, int EPI>
+template <int D, int NT, bool LN_A, int EPI, int MS = 4>
 __device__ void dec_tile(const DecArParams& p, unsigned char* smem, const __nv_bfloat16* __restrict__ A, int lda,
                          const float* __restrict__ ysrc, const float* __restrict__ gamma, const float* __restrict__ beta,
                          const __nv_bfloat16* __restrict__ W, int K, int N, const float* __restrict__ bias, int row0, int n0,
                          int step, int ldw = 0, int split = 0, const float* __restrict__ addp = nullptr) {
   // ldw: row pitch of W (elements) when only a K-slice of it is multiplied (split-K), 0 -> K.
   // addp: LN_A only - DEC_KSPLIT extra fp32 [M, D] arrays added (in fixed order) to ysrc before normalising.
-  constexpr int BN = 16 * NT;
+  // MS = 4: 64-row tile, warp w -> slab (w & 3), column half (w >> 2);  MS = 1: 16-row tile, warp w -> columns only
+  constexpr int NWN = 8 / MS;                 // warps along N
+  constexpr int BN = 8 * NT * NWN;
+  constexpr int TM = 16 * MS;                 // rows per tile
   const int wld = ldw ? ldw : K;
   static_assert(BN <= DEC_MAX_BN, "tile width");
   __nv_bfloat16* a_res = reinterpret_cast<__nv_bfloat16*>(smem);                        // [D/64][4096]
   __nv_bfloat16* a_st = a_res + (D / 64) * 4096;                                         // [STAGES][4096]
   __nv_bfloat16* w_st = a_st + DEC_STAGES * 4096;                                        // [STAGES][BN*64]
-  float* s_log = reinterpret_cast<float*>(w_st + DEC_STAGES * DEC_MAX_BN * 64);          // [64][96] (head only)
+  float* s_log = reinterpret_cast<float*>(w_st + DEC_STAGES * DEC_MAX_BN * 64);          // [64][128] (head only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.B;
   const int nkb = K / 64;
@@ -118,7 +121,7 @@ __device__ void dec_tile(const DecArParams& p, unsigned char* smem, const __nv_b
       cp_async_16(smem_u32(w_st + stage * (BN * 64) + swz64(r, ck * 8)), W + static_cast<long long>(n) * wld + kb * 64 + ck * 8);
     }
     if (!LN_A) {
-      for (int i = tid; i < 64 * 8; i += DEC_THREADS) {
+      for (int i = tid; i < TM * 8; i += DEC_THREADS) {
         const int r = i >> 3, ck = i & 7;
         int m = row0 + r;
         if (m >= M) m = M - 1;
@@ -190,16 +193,19 @@ __device__ void dec_tile(const DecArParams& p, unsigned char* smem, const __nv_b
         }
       }
     };
-    if (addp != nullptr) {
+    constexpr int RPW = TM / 8;               // rows per warp
+    if (RPW == 2) {
+      ln_rows(std::integral_constant<int, 2>{}, 0);
+    } else if (addp != nullptr) {
 #pragma unroll 1
-      for (int f = 0; f < 8; f += 2) ln_rows(std::integral_constant<int, 2>{}, f);
+      for (int f = 0; f < RPW; f += 2) ln_rows(std::integral_constant<int, 2>{}, f);
     } else {
 #pragma unroll 1
-      for (int f = 0; f < 8; f += 4) ln_rows(std::integral_constant<int, 4>{}, f);
+      for (int f = 0; f < RPW; f += 4) ln_rows(std::integral_constant<int, 4>{}, f);
     }
   }
 
-  const int ms = warp & 3, nh = warp >> 2;
+  const int ms = (MS == 4) ? (warp & 3) : 0, nh = (MS == 4) ? (warp >> 2) : warp;
   float acc[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -242,20 +248,20 @@ __device__ void dec_tile(const DecArParams& p, unsigned char* smem, const __nv_b
     for (int nt = 0; nt < NT; ++nt) {
       const int c = (nh * NT + nt) * 8 + 2 * t;     // column inside the 96-wide tile
       const float b0 = (c < N) ? __ldg(bias + c) : 0.f, b1 = (c + 1 < N) ? __ldg(bias + c + 1) : 0.f;
-      s_log[(ms * 16 + g) * 96 + c] = acc[nt][0] + b0;
-      s_log[(ms * 16 + g) * 96 + c + 1] = acc[nt][1] + b1;
-      s_log[(ms * 16 + g + 8) * 96 + c] = acc[nt][2] + b0;
-      s_log[(ms * 16 + g + 8) * 96 + c + 1] = acc[nt][3] + b1;
+      s_log[(ms * 16 + g) * 128 + c] = acc[nt][0] + b0;
+      s_log[(ms * 16 + g) * 128 + c + 1] = acc[nt][1] + b1;
+      s_log[(ms * 16 + g + 8) * 128 + c] = acc[nt][2] + b0;
+      s_log[(ms * 16 + g + 8) * 128 + c + 1] = acc[nt][3] + b1;
     }
     __syncthreads();
-    for (int r = warp; r < 64; r += 8) {
+    for (int r = warp; r < TM; r += 8) {
       const int m = row0 + r;
       if (m >= M) continue;                          // warp-uniform
       float* lrow = p.logits + (static_cast<long long>(m) * p.L + step) * p.C;
       float best = -INFINITY;
       int bi = 0x7fffffff;
       for (int j = lane; j < N; j += 32) {
-        const float v = s_log[r * 96 + j];
+        const float v = s_log[r * 128 + j];
         lrow[j] = v;
         if (v > best) { best = v; bi = j; }
       }
@@ -357,6 +363,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
         for (int j = 0; j < 32; ++j) kreg[j] = 0.f;
       }
       const float qv = __ldg(p.qs + static_cast<long long>(step) * D + h * 32 + lane);
+      float vreg[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {      // V gathers issued together with the K loads: one L2 round trip per item
+        const int idk = __shfl_sync(0xffffffffu, myid, k);
+        vreg[k] = (k < nkeys) ? __bfloat162float(p.kvtab[(static_cast<long long>(k) * p.V + idk) * 2 * D + D + h * 32 + lane]) : 0.f;
+      }
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) s = fmaf(__shfl_sync(0xffffffffu, qv, j), kreg[j], s);
@@ -369,12 +381,6 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float pme = e / sum;
-      float vreg[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {      // independent gathers: all in flight before the first use
-        const int idk = __shfl_sync(0xffffffffu, myid, k);
-        vreg[k] = (k < nkeys) ? __bfloat162float(p.kvtab[(static_cast<long long>(k) * p.V + idk) * 2 * D + D + h * 32 + lane]) : 0.f;
-      }
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, pme, k), vreg[k], acc);
@@ -391,9 +397,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
     grid_barrier(p.bar, target);
     DEC_PROF(4);
     // ---------------- P3: qc = scale * q_proj(LN1(y)) ----------------
-    for (int tile = blockIdx.x; tile < mt * (D / 64); tile += gridDim.x)
-      dec_tile<D, 4, true, DE_SCALE>(p, dec_smem, nullptr, 0, p.y, p.g1, p.be1, p.Wq_c, D, D, p.bq_c, (tile / (D / 64)) * 64,
-                                     (tile % (D / 64)) * 64, step);
+    {
+      const int mt16 = (p.B + 15) / 16, ntq = D / 128;
+      for (int tile = blockIdx.x; tile < mt16 * ntq; tile += gridDim.x)
+        dec_tile<D, 2, true, DE_SCALE, 1>(p, dec_smem, nullptr, 0, p.y, p.g1, p.be1, p.Wq_c, D, D, p.bq_c, (tile / ntq) * 16,
+                                          (tile % ntq) * 128, step);
+    }
     DEC_PROF(5);
     grid_barrier(p.bar, target);
     DEC_PROF(6);
@@ -417,6 +426,16 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
           for (int j = 0; j < 16; ++j) kw[r][j] = 0u;
         }
       }
+      // V tiles (16-byte loads) are requested together with K: lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3),
+      // 16 loads cover the 128 keys
+      const int kg = lane >> 2, cc = lane & 3;
+      const __nv_bfloat16* vb = kvb + D + h * 32 + cc * 8;
+      uint4 vv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int key = i * 8 + kg;
+        vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
+      }
       const float qv = p.qc[static_cast<long long>(b) * D + h * 32 + lane];
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -438,34 +457,20 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
       float sum = (e0 + e1) + (e2 + e3);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      // P.V with 16-byte loads: lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3); 16 iterations cover the
-      // 128 keys, then the 8 key groups are summed with xor-shuffles; lanes 0..3 hold the 32 output channels.
-      const int kg = lane >> 2, cc = lane & 3;
-      const __nv_bfloat16* vb = kvb + D + h * 32 + cc * 8;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint4 vv[8];
+      for (int it = 0; it < 16; ++it) {                // key = it*8 + kg -> register e_(it>>2), source lane (it&3)*8 + kg
+        const int src = (it & 3) * 8 + kg;
+        const float er = (it >> 2) == 0 ? e0 : (it >> 2) == 1 ? e1 : (it >> 2) == 2 ? e2 : e3;
+        const float pk = __shfl_sync(0xffffffffu, er, src);
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&vv[it]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int key = (half * 8 + i) * 8 + kg;
-          vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int it = half * 8 + i;                 // key = it*8 + kg -> register e_(it>>2), source lane (it&3)*8 + kg
-          const int src = (it & 3) * 8 + kg;
-          const float er = (it >> 2) == 0 ? e0 : (it >> 2) == 1 ? e1 : (it >> 2) == 2 ? e2 : e3;
-          const float pk = __shfl_sync(0xffffffffu, er, src);
-          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&vv[i]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(p2[e]);
-            o[e * 2] = fmaf(pk, f.x, o[e * 2]);
-            o[e * 2 + 1] = fmaf(pk, f.y, o[e * 2 + 1]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(p2[e]);
+          o[e * 2] = fmaf(pk, f.x, o[e * 2]);
+          o[e * 2 + 1] = fmaf(pk, f.y, o[e * 2 + 1]);
         }
       }
 #pragma unroll
@@ -515,8 +520,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
     grid_barrier(p.bar, target);
     DEC_PROF(14);
     // ---------------- P8: logits[:, step] = head(LN3(y)); ids[:, step+1] = argmax ----------------
-    for (int tile = blockIdx.x; tile < mt; tile += gridDim.x)
-      dec_tile<D, 6, true, DE_HEAD>(p, dec_smem, nullptr, 0, p.y, p.g3, p.be3, p.Wh, D, p.C, p.bh, tile * 64, 0, step, 0, 0, p.part);
+    {
+      const int mt16 = (p.B + 15) / 16;
+      for (int tile = blockIdx.x; tile < mt16; tile += gridDim.x)
+        dec_tile<D, 2, true, DE_HEAD, 1>(p, dec_smem, nullptr, 0, p.y, p.g3, p.be3, p.Wh, D, p.C, p.bh, tile * 16, 0, step, 0, 0,
+                                         p.part);
+    }
     DEC_PROF(15);
     grid_barrier(p.bar, target);
   }
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
 
 template <int D>
 constexpr size_t dec_ar_smem_bytes() {
-  return static_cast<size_t>((D / 64) * 4096 + DEC_STAGES * 4096 + DEC_STAGES * DEC_MAX_BN * 64) * 2 + 64 * 96 * 4;
+  return static_cast<size_t>((D / 64) * 4096 + DEC_STAGES * 4096 + DEC_STAGES * DEC_MAX_BN * 64) * 2 + 64 * 128 * 4;
 }
 
 }  // namespace pq

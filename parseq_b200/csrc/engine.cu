@@ -173,6 +173,7 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   PQ_TRY((warm_gemm_cfg<64, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 1>()));
+  PQ_TRY((warm_gemm_cfg<192, 1>()));
   PQ_TRY((warm_gemm_cfg<256, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 2>()));
   PQ_TRY((warm_gemm_cfg<192, 2>()));
@@ -189,18 +190,18 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
     PQ_CUDA(cudaGetDevice(&dev));
     PQ_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  // Tile choice from tests/bench_gemm.py on B200 (profiles/r1_gemm_microbench.txt): single-CTA 128 x 256 tiles win
-  // for the wide projections (QKV 1152 -> 4.5 tiles, fc1 1536, fc2/K=1536), 128 x 128 for N = 384 and for the small
-  // decoder GEMMs; the CTA-pair variant (cta_group::2) is correct but slower with this pipeline depth, so it is opt-in.
+  // Tile choice from tests/bench_gemm.py on B200 (profiles/r1_gemm_microbench*.txt): single-CTA 128 x 256 tiles win
+  // for the wide projections (QKV 1152 -> 4.5 tiles, fc1 1536), 128 x 192 for N = 384 / 768 (no padded columns),
+  // 128 x 128 for the small decoder GEMMs; the CTA-pair variant (cta_group::2) is correct but slower with this pipeline depth, so it is opt-in.
   int CG = 1;
   if (g_cta_group_override) CG = g_cta_group_override;
   int BN;
   if (CG == 2) BN = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : 128;
-  else BN = (N <= 64) ? 64 : (M >= 1024 && (N >= 1024 || (N % 256 == 0 && K >= 1024))) ? 256 : 128;
+  else BN = (N <= 64) ? 64 : (M < 1024) ? 128 : (N >= 1024) ? 256 : (N % 192 == 0) ? 192 : 128;
   if (g_block_n_override) {
     BN = g_block_n_override;
     if (CG == 2 && BN == 64) BN = 128;
-    if (CG == 1 && BN == 192) BN = 128;
+
   }
   CUtensorMap ta, tb, tc;
   PQ_TRY(make_tmap(&ta, A, 2, M, K, lda, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
@@ -234,6 +235,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
     return launch_gemm_cfg<128, 2>(ta, tb, tc, p, tiles, st);
   }
   if (BN == 256) return launch_gemm_cfg<256, 1>(ta, tb, tc, p, tiles, st);
+  if (BN == 192) return launch_gemm_cfg<192, 1>(ta, tb, tc, p, tiles, st);
   if (BN == 64) return launch_gemm_cfg<64, 1>(ta, tb, tc, p, tiles, st);
   return launch_gemm_cfg<128, 1>(ta, tb, tc, p, tiles, st);
 }
