@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--dec-chunk", type=int, default=0, help="images per decoder chain (0 = engine default 128)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--attn-impl", type=int, default=-1, help="encoder attention: 1 tcgen05 (default), 0 mma.sync")
     ap.add_argument("--no-ar-kernel", action="store_true", help="AR loop as separate kernels instead of the persistent kernel")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM tile: 0 auto, 1 single CTA, 2 CTA pair")
     ap.add_argument("--block-n", type=int, default=0)
@@ -222,6 +223,8 @@ def main():
         model.model.set_engine_option("use_graph", 0)
     if args.no_pdl:
         model.model.set_engine_option("pdl", 0)
+    if args.attn_impl >= 0:
+        model.model.set_engine_option("attn_impl", args.attn_impl)
     if args.no_ar_kernel:
         model.model.set_engine_option("ar_kernel", 0)
     if args.cta_group:

@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "dec_ar.cuh"
+#include "attn_tc.cuh"
 
 namespace {
 
@@ -165,6 +166,7 @@ int ln_head_argmax_launch(const float* y, const float* g, const float* b, float 
 }
 
 int init_kernel_attributes() {
+  PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::ATC_SMEM_BYTES));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<192>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
@@ -253,9 +255,22 @@ int layernorm_launch(const float* x, const float* g, const float* b, float eps, 
   }
 }
 
+int g_attn_impl = 1;   // 1: tcgen05 kernel (attn_tc.cuh), 0: mma.sync kernel (kernels.cuh)
+
 int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
   if (T != pq::ATT_T || D != heads * pq::ATT_DH)
     return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernel covers T=128 tokens, head_dim=64");
+  if (g_attn_impl == 1) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::ATC_SMEM_BYTES));
+      attr_set = true;
+    }
+    CUtensorMap tq, to;
+    PQ_TRY(make_tmap(&tq, qkv, 2, static_cast<long long>(B) * T, 3ll * D, 3ll * D, 64, 128));
+    PQ_TRY(make_tmap(&to, out, 2, static_cast<long long>(B) * T, D, D, 64, 32));
+    return launch_k(pq::enc_attention_tc_kernel, dim3(B * heads), dim3(pq::ATC_THREADS), pq::ATC_SMEM_BYTES, st, tq, to, D, heads);
+  }
   return launch_k(pq::enc_attention_kernel, dim3(B * heads), dim3(256), 0, st,
                   reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), D, heads);
 }
@@ -998,6 +1013,7 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     g_block_n_override = static_cast<int>(value);
     return PARSEQ_OK;
   }
+  if (n == "attn_impl") { g_attn_impl = value != 0 ? 1 : 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "pdl") { g_use_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
   if (n == "cta_group") {

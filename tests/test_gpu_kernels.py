@@ -158,9 +158,11 @@ def test_layernorm(lib, D, eps):
     assert (y.float() == y32.bfloat16().float()).all()
 
 
-@pytest.mark.parametrize("B,heads", [(1, 6), (5, 6), (3, 3), (2, 12)])
-def test_enc_attention(lib, B, heads):
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("B,heads", [(1, 6), (5, 6), (3, 3), (2, 12), (300, 6)])
+def test_enc_attention(lib, B, heads, impl):
     from parseq_b200.engine import check
+    check(lib, lib.parseq_set_option(None, b"attn_impl", impl))
     T, d = 128, 64
     D = heads * d
     g = torch.Generator(device="cuda").manual_seed(B * 10 + heads)
@@ -174,4 +176,5 @@ def test_enc_attention(lib, B, heads):
     o = (e.bfloat16().float() @ v) / e.sum(-1, keepdim=True)
     ref = o.permute(0, 2, 1, 3).reshape(B * T, D)
     err = (out.float() - ref).abs().max().item()
+    check(lib, lib.parseq_set_option(None, b"attn_impl", 1))
     assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err
