@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 4) enc_attention_tc_kernel(const 
         float f[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          f[t] = exp2f((__uint_as_float(v[jj * 8 + t]) - mx) * kScaleLog2);
+          f[t] = ex2_approx((__uint_as_float(v[jj * 8 + t]) - mx) * kScaleLog2);
           sum += f[t];
         }
         uint4 q;

@@ -364,10 +364,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
       }
       const float qv = __ldg(p.qs + static_cast<long long>(step) * D + h * 32 + lane);
       float vreg[32];
+      // element offset of key `lane`'s V row segment for this head (one multiply per lane instead of one per key)
+      const int voff = (lane * p.V + myid) * (2 * D) + D + h * 32;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {      // V gathers issued together with the K loads: one L2 round trip per item
-        const int idk = __shfl_sync(0xffffffffu, myid, k);
-        vreg[k] = (k < nkeys) ? __bfloat162float(p.kvtab[(static_cast<long long>(k) * p.V + idk) * 2 * D + D + h * 32 + lane]) : 0.f;
+        const int ok = __shfl_sync(0xffffffffu, voff, k);
+        vreg[k] = (k < nkeys) ? __bfloat162float(p.kvtab[ok + lane]) : 0.f;
       }
       float s = 0.f;
 #pragma unroll

@@ -509,8 +509,10 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
   e->cur_cat = CAT_DEC_GEMM;
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
-    PQ_TRY(launch_k(pq::dec_self_attn2_kernel, dim3(B), dim3(D), 0, st, static_cast<const float*>(e->qs),
-                    static_cast<const __nv_bfloat16*>(e->kvtab), ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa));
+    const int qsplit = (nq >= 8) ? 4 : 1;
+    PQ_TRY(launch_k(pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D), 0, st, static_cast<const float*>(e->qs),
+                    static_cast<const __nv_bfloat16*>(e->kvtab), ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa,
+                    qsplit));
   }
   // y = pos_queries[q0+qi] + out_proj(sa): the GEMM stores out_proj(sa) with its TMA epilogue, the LayerNorm kernel
   // adds the (broadcast) query residual, writes y back and emits norm1(y)
@@ -531,7 +533,13 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
               1.0f, nullptr, 0, 0, sg.hd, e->Md, st));
   PQ_TRY(gemm(e, sg.hd, e->Md, e->w(Ly + "linear2.weight"), e->Md, e->wf(Ly + "linear2.bias"), M, D, e->Md, pq::EPI_F32,
               1.0f, sg.y, D, 0, sg.y, D, st));
-  {
+  if (nq > 1 && ids_dst == nullptr) {
+    // multi-query passes (refine / NAR): LayerNorm kernel + tcgen05 GEMM for the head (weights read once per tile).
+    // Chosen by pass type, not by batch size, so that a row's result does not depend on the batch it is computed in.
+    PQ_TRY(layernorm(e, sg.y, "decoder.norm", 1e-5f, M, sg.yn, nullptr, st));
+    PQ_TRY(gemm(e, sg.yn, D, e->w("head.weight"), D, e->wf("head.bias"), M, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0,
+                logits_out, logits_ld, st));
+  } else {
     TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * M * e->C * D);
     PQ_TRY(ln_head_argmax_launch(sg.y, e->wf("decoder.norm.weight"), e->wf("decoder.norm.bias"), 1e-5f, e->wb("head.weight"),
                                  e->wf("head.bias"), M, e->C, D, logits_out, logits_ld, ids_dst, 32, nq, dst_off, forced,

@@ -27,7 +27,16 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16
     const int b = static_cast<int>(t);
     const float* src = img + ((static_cast<long long>(b) * 3 + ch) * H + (r * ph + dy)) * W + c * pw;
     __nv_bfloat16* dst = out + (static_cast<long long>(b) * gh * gw + r * gw + c) * Kp + ch * ph * pw + dy * pw;
-    for (int dx = 0; dx < pw; ++dx) dst[dx] = __float2bfloat16_rn(src[dx]);
+    if (pw == 8 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      uint4 q;
+      q.x = pack_bf16(a.x, a.y); q.y = pack_bf16(a.z, a.w);
+      q.z = pack_bf16(d.x, d.y); q.w = pack_bf16(d.z, d.w);
+      *reinterpret_cast<uint4*>(dst) = q;
+    } else {
+      for (int dx = 0; dx < pw; ++dx) dst[dx] = __float2bfloat16_rn(src[dx]);
+    }
   }
 }
 
@@ -427,12 +436,14 @@ __global__ void set_int_kernel(int* p, int v) {
 // dec_self_attn_kernel (kept for reference / tests).
 __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
                                       const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
-                                      int mode, int eos_id, __nv_bfloat16* __restrict__ out) {
+                                      int mode, int eos_id, __nv_bfloat16* __restrict__ out, int qsplit) {
+  // grid = B * qsplit: CTA (b, part) handles queries [part*nq/qsplit, (part+1)*nq/qsplit) of image b
   __shared__ int s_ids[32];
   __shared__ int s_first_eos;
   grid_dep_launch();
   grid_dep_wait();
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / qsplit, part = blockIdx.x % qsplit;
+  const int q_begin = (part * nq) / qsplit, q_end = ((part + 1) * nq) / qsplit;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {
     const int id = (threadIdx.x < nkeys) ? ids[static_cast<long long>(b) * ids_ld + threadIdx.x] : -1;
@@ -463,7 +474,7 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
 #pragma unroll
   for (int k = 0; k < 32; ++k)
     vreg[k] = (k < nkeys) ? __bfloat162float(kvtab[(static_cast<long long>(k) * V + s_ids[k]) * 2 * D + D + h * 32 + lane]) : 0.f;
-  for (int qi = 0; qi < nq; ++qi) {
+  for (int qi = q_begin; qi < q_end; ++qi) {
     const int qpos = q0 + qi;
     const float qv = __ldg(Qs + static_cast<long long>(qpos) * D + h * 32 + lane);   // lane j holds q_j
     float s = 0.f;
@@ -547,15 +558,39 @@ __global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __res
     float sum = (e0 + e1) + (e2 + e3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    float acc = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      acc = fmaf(__shfl_sync(0xffffffffu, e0, k), __bfloat162float(sV[k * 32 + lane]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e1, k), __bfloat162float(sV[(32 + k) * 32 + lane]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e2, k), __bfloat162float(sV[(64 + k) * 32 + lane]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e3, k), __bfloat162float(sV[(96 + k) * 32 + lane]), acc);
+    // P.V with 16-byte smem reads: lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3); 16 iterations cover
+    // the 128 keys; the 8 key groups are then summed with xor-shuffles and lanes 0..3 hold the 32 output channels.
+    const int kg = lane >> 2, cc = lane & 3;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {                  // key = it*8 + kg -> register e_(it>>2), source lane (it&3)*8 + kg
+      const int key = it * 8 + kg;
+      const uint4 vvv = *reinterpret_cast<const uint4*>(sV + key * 32 + cc * 8);
+      const float er = (it >> 2) == 0 ? e0 : (it >> 2) == 1 ? e1 : (it >> 2) == 2 ? e2 : e3;
+      const float pk = __shfl_sync(0xffffffffu, er, (it & 3) * 8 + kg);
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&vvv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(p2[e]);
+        o[e * 2] = fmaf(pk, f.x, o[e * 2]);
+        o[e * 2 + 1] = fmaf(pk, f.y, o[e * 2 + 1]);
+      }
     }
-    out[row * D + h * 32 + lane] = __float2bfloat16_rn(acc * (1.0f / sum));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] += __shfl_xor_sync(0xffffffffu, o[j], 4);
+      o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+      o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+    }
+    if (kg == 0) {
+      const float inv = 1.0f / sum;
+      uint4 q4;
+      q4.x = pack_bf16(o[0] * inv, o[1] * inv); q4.y = pack_bf16(o[2] * inv, o[3] * inv);
+      q4.z = pack_bf16(o[4] * inv, o[5] * inv); q4.w = pack_bf16(o[6] * inv, o[7] * inv);
+      *reinterpret_cast<uint4*>(out + row * D + h * 32 + cc * 8) = q4;
+    }
   }
 }
 
