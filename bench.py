@@ -315,10 +315,16 @@ def main():
     # The GEMM kernel is timed inside a long step -> sustained cuBLAS figure is the denominator
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     total_timed = sum(v["ms"] for v in tim.values())
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_ncu_traffic.json")
+    if os.path.exists(tpath):          # dram__bytes_read+write per launch of the GEMM kernel from the committed ncu capture
+        with open(tpath) as f:
+            traffic = json.load(f).get("avg_dram_bytes_per_launch")
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (encoder projections)",
         "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
-        "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+        "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
+        "traffic_source": "profiles/r1_gemm_ncu_traffic.json (ncu --set full, avg dram bytes per launch of QKV/proj/fc1/fc2)",
         "flops_per_launch": enc["flops"] / max(1, enc["launches"]),
         "avg_launch_ms": enc["ms"] / max(1, enc["launches"]),
         "share_of_step": enc["ms"] / total_timed if total_timed else None,
