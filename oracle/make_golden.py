@@ -39,6 +39,10 @@ CASES = [
     ("s_eos_nar2_b4",   "parseq",      1, 0.5, 4, 8, False, 2, None),
     ("ti_nar0_b1",      "parseq-tiny", 2, 0.0, 1, 9, False, 0, None),
     ("ti_ar1_b3",       "parseq-tiny", 2, 0.0, 3, 10, True, 1, None),
+    # other geometries: T = 196 tokens (224x224 / 16x16) and the BASELINE ViT-B-width stress config (48x160, T = 240, D = 768)
+    ("p16_ar1_b2",      "parseq-patch16-224", 3, 0.0, 2, 11, True, 1, None),
+    ("p16_nar1_b1",     "parseq-patch16-224", 3, 0.0, 1, 12, False, 1, None),
+    ("b48_ar1_b2",      "parseq-base-48x160", 4, 0.0, 2, 13, True, 1, None),
 ]
 
 

@@ -315,7 +315,7 @@ __device__ void dec_tile(const DecArParams& p, unsigned char* smem, const __nv_b
   }
 }
 
-template <int D>
+template <int D, int TB>   // TB = number of 128-key blocks of the image memory (T <= 128*TB)
 __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParams p) {
   extern __shared__ __align__(128) unsigned char dec_smem[];
   grid_dep_launch();
@@ -408,71 +408,90 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
     DEC_PROF(5);
     grid_barrier(p.bar, target);
     DEC_PROF(6);
-    // ---------------- P4: cross-attention, warp per (image, head), T = 128 keys ----------------
+    // ---------------- P4: cross-attention, warp per (image, head), T <= 128*TB keys ----------------
     for (int item = gwarp; item < p.B * p.heads; item += nwarps) {
       const int b = item / p.heads, h = item % p.heads;
       const __nv_bfloat16* kvb = p.ckv + static_cast<long long>(b) * p.T * 2 * D;
-      uint32_t kw[4][16];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int key = r * 32 + lane;
-        if (key < p.T) {
-          const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * D + h * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = __ldg(kr + j);
-            kw[r][j * 4] = u.x; kw[r][j * 4 + 1] = u.y; kw[r][j * 4 + 2] = u.z; kw[r][j * 4 + 3] = u.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) kw[r][j] = 0u;
-        }
-      }
-      // V tiles (16-byte loads) are requested together with K: lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3),
-      // 16 loads cover the 128 keys
+      // lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3) for the 16-byte V loads
       const int kg = lane >> 2, cc = lane & 3;
       const __nv_bfloat16* vb = kvb + D + h * 32 + cc * 8;
+      const float qv = p.qc[static_cast<long long>(b) * D + h * 32 + lane];
+      float sc[4 * TB];
       uint4 vv[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int key = i * 8 + kg;
-        vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      const float qv = p.qc[static_cast<long long>(b) * D + h * 32 + lane];
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int blk = 0; blk < TB; ++blk) {
+        uint32_t kw[4][16];
 #pragma unroll
-      for (int w = 0; w < 16; ++w) {
-        const float qa = __shfl_sync(0xffffffffu, qv, 2 * w), qb = __shfl_sync(0xffffffffu, qv, 2 * w + 1);
-        s0 = fmaf(qb, __uint_as_float(kw[0][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[0][w] << 16), s0));
-        s1 = fmaf(qb, __uint_as_float(kw[1][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[1][w] << 16), s1));
-        s2 = fmaf(qb, __uint_as_float(kw[2][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[2][w] << 16), s2));
-        s3 = fmaf(qb, __uint_as_float(kw[3][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[3][w] << 16), s3));
+        for (int r = 0; r < 4; ++r) {
+          const int key = blk * 128 + r * 32 + lane;
+          if (key < p.T) {
+            const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * D + h * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(kr + j);
+              kw[r][j * 4] = u.x; kw[r][j * 4 + 1] = u.y; kw[r][j * 4 + 2] = u.z; kw[r][j * 4 + 3] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) kw[r][j] = 0u;
+          }
+        }
+        if (TB == 1) {   // single block: request V together with K (one L2 round trip per item)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int key = i * 8 + kg;
+            vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const float qa = __shfl_sync(0xffffffffu, qv, 2 * w), qb = __shfl_sync(0xffffffffu, qv, 2 * w + 1);
+          s0 = fmaf(qb, __uint_as_float(kw[0][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[0][w] << 16), s0));
+          s1 = fmaf(qb, __uint_as_float(kw[1][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[1][w] << 16), s1));
+          s2 = fmaf(qb, __uint_as_float(kw[2][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[2][w] << 16), s2));
+          s3 = fmaf(qb, __uint_as_float(kw[3][w] & 0xffff0000u), fmaf(qa, __uint_as_float(kw[3][w] << 16), s3));
+        }
+        sc[blk * 4 + 0] = (blk * 128 + lane < p.T) ? s0 : -INFINITY;
+        sc[blk * 4 + 1] = (blk * 128 + 32 + lane < p.T) ? s1 : -INFINITY;
+        sc[blk * 4 + 2] = (blk * 128 + 64 + lane < p.T) ? s2 : -INFINITY;
+        sc[blk * 4 + 3] = (blk * 128 + 96 + lane < p.T) ? s3 : -INFINITY;
       }
-      if (lane >= p.T) s0 = -INFINITY;
-      if (32 + lane >= p.T) s1 = -INFINITY;
-      if (64 + lane >= p.T) s2 = -INFINITY;
-      if (96 + lane >= p.T) s3 = -INFINITY;
-      float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+      float mx = sc[0];
+#pragma unroll
+      for (int r = 1; r < 4 * TB; ++r) mx = fmaxf(mx, sc[r]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float e0 = expf(s0 - mx), e1 = expf(s1 - mx), e2 = expf(s2 - mx), e3 = expf(s3 - mx);
-      float sum = (e0 + e1) + (e2 + e3);
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4 * TB; ++r) {
+        sc[r] = expf(sc[r] - mx);
+        sum += sc[r];
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {                // key = it*8 + kg -> register e_(it>>2), source lane (it&3)*8 + kg
-        const int src = (it & 3) * 8 + kg;
-        const float er = (it >> 2) == 0 ? e0 : (it >> 2) == 1 ? e1 : (it >> 2) == 2 ? e2 : e3;
-        const float pk = __shfl_sync(0xffffffffu, er, src);
-        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&vv[it]);
+      for (int blk = 0; blk < TB; ++blk) {
+        if (TB != 1) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(p2[e]);
-          o[e * 2] = fmaf(pk, f.x, o[e * 2]);
-          o[e * 2 + 1] = fmaf(pk, f.y, o[e * 2 + 1]);
+          for (int i = 0; i < 16; ++i) {
+            const int key = blk * 128 + i * 8 + kg;
+            vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {              // key = blk*128 + it*8 + kg -> sc[blk*4 + (it>>2)], lane (it&3)*8 + kg
+          const float pk = __shfl_sync(0xffffffffu, sc[blk * 4 + (it >> 2)], (it & 3) * 8 + kg);
+          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&vv[it]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(p2[e]);
+            o[e * 2] = fmaf(pk, f.x, o[e * 2]);
+            o[e * 2 + 1] = fmaf(pk, f.y, o[e * 2 + 1]);
+          }
         }
       }
 #pragma unroll

@@ -167,9 +167,12 @@ int ln_head_argmax_launch(const float* y, const float* g, const float* b, float 
 
 int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::ATC_SMEM_BYTES));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<192>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<192>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<192>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -258,8 +261,11 @@ int layernorm_launch(const float* x, const float* g, const float* b, float eps, 
 int g_attn_impl = 1;   // 1: tcgen05 kernel (attn_tc.cuh), 0: mma.sync kernel (kernels.cuh)
 
 int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
-  if (T != pq::ATT_T || D != heads * pq::ATT_DH)
-    return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernel covers T=128 tokens, head_dim=64");
+  if (D != heads * pq::ATT_DH) return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernels cover head_dim=64");
+  if (T != pq::ATT_T) {   // general token count: masked two-pass mma.sync kernel
+    return launch_k(pq::enc_attention_any_kernel, dim3(B * heads, (T + pq::ATT_T - 1) / pq::ATT_T), dim3(256), 0, st,
+                    reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), T, D, heads);
+  }
   if (g_attn_impl == 1) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -510,7 +516,7 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
     const int qsplit = (nq >= 8) ? 4 : 1;
-    PQ_TRY(launch_k(pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D), 0, st, static_cast<const float*>(e->qs),
+    PQ_TRY(launch_k(pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D < 384 ? D : 384), 0, st, static_cast<const float*>(e->qs),
                     static_cast<const __nv_bfloat16*>(e->kvtab), ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa,
                     qsplit));
   }
@@ -523,8 +529,12 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
   PQ_TRY(gemm(e, sg.yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, sg.qc, D, st));
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
-    PQ_TRY(launch_k(pq::dec_cross_attn3_kernel, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
-                    static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
+    if (e->T <= 128)
+      PQ_TRY(launch_k(pq::dec_cross_attn3_kernel<4>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
+                      static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
+    else
+      PQ_TRY(launch_k(pq::dec_cross_attn3_kernel<8>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
+                      static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
   }
   PQ_TRY(gemm(e, sg.ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
               pq::EPI_F32, 1.0f, sg.y, D, 0, sg.y, D, st));
@@ -633,9 +643,18 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
     TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * macs);
     const dim3 grid(static_cast<unsigned>(g_sm_count)), block(pq::DEC_THREADS);
     switch (D) {
-      case 192: PQ_TRY(launch_k(pq::dec_ar_kernel<192>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p)); break;
-      case 384: PQ_TRY(launch_k(pq::dec_ar_kernel<384>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p)); break;
-      case 768: PQ_TRY(launch_k(pq::dec_ar_kernel<768>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p)); break;
+      case 192:
+        if (e->T <= 128) PQ_TRY(launch_k(pq::dec_ar_kernel<192, 1>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p));
+        else PQ_TRY(launch_k(pq::dec_ar_kernel<192, 2>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p));
+        break;
+      case 384:
+        if (e->T <= 128) PQ_TRY(launch_k(pq::dec_ar_kernel<384, 1>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p));
+        else PQ_TRY(launch_k(pq::dec_ar_kernel<384, 2>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p));
+        break;
+      case 768:
+        if (e->T <= 128) PQ_TRY(launch_k(pq::dec_ar_kernel<768, 1>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p));
+        else PQ_TRY(launch_k(pq::dec_ar_kernel<768, 2>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p));
+        break;
       default: return fail(PARSEQ_ERR_UNSUPPORTED, "dec_ar: embed_dim must be 192, 384 or 768");
     }
   }
@@ -813,9 +832,9 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   // encoder GEMMs occupy every SM, so splitting into stages only shrinks the GEMMs ("chunk" option re-enables it).
   e->chunk = e->max_batch;
   e->dec_chunk = e->max_batch < 128 ? e->max_batch : 128;
-  if (e->T != 128) {
+  if (e->T > 256) {
     delete e;
-    return fail(PARSEQ_ERR_UNSUPPORTED, "this build covers 128-token images (32x128 / patch 4x8)");
+    return fail(PARSEQ_ERR_UNSUPPORTED, "at most 256 image tokens (img_size / patch_size) are supported");
   }
   if ((e->Kp * 2) % 16 != 0) { delete e; return fail(PARSEQ_ERR_UNSUPPORTED, "patch dim must be a multiple of 8"); }
   // ---- weight slots: state_dict keys of strhub.models.parseq.model.PARSeq ----

@@ -227,6 +227,137 @@ __global__ void __launch_bounds__(256, 2) enc_attention_kernel(const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------
+// ViT attention core for ANY token count T (e.g. 196 = 224x224/16x16, 240 = 48x160/4x8), head dim 64: correctness
+// path for the geometries that do not fill one 128-row tile per image (the T = 128 fast path is attn_tc.cuh).
+// grid = (B*heads, ceil(T/128)): one CTA per 128-query tile; keys are visited in blocks of 128 in two passes
+// (pass 1: row maxima, pass 2: P = exp(S - max), O += P V) so the rounding points equal the single-tile kernel's.
+// Rows / keys >= T are masked; same mma.sync fragment scheme as enc_attention_kernel.
+__global__ void __launch_bounds__(256, 2) enc_attention_any_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                   __nv_bfloat16* __restrict__ out, int T, int D,
+                                                                   int heads) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ __align__(128) __nv_bfloat16 sQ[ATT_T * ATT_DH];
+  __shared__ __align__(128) __nv_bfloat16 sK[ATT_T * ATT_DH];
+  __shared__ __align__(128) __nv_bfloat16 sV[ATT_T * ATT_DH];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int q0 = blockIdx.y * ATT_T;                         // first query row of this tile
+  const int nkb = (T + ATT_T - 1) / ATT_T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long ld = 3ll * D;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * ld + h * ATT_DH;
+  auto load_tile = [&](__nv_bfloat16* dst, int mat, int row0) {   // rows clamped to T-1 (masked later)
+    for (int i = tid; i < ATT_T * 8; i += 256) {
+      const int r = i >> 3, ck = i & 7;
+      int row = row0 + r;
+      if (row >= T) row = T - 1;
+      cp_async_16(smem_u32(dst + att_swz(r, ck * 8)), base + static_cast<long long>(row) * ld + mat * D + ck * 8);
+    }
+  };
+  load_tile(sQ, 0, q0);
+  cp_async_wait_all();
+  __syncthreads();
+  const int r0 = warp * 16;
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int col = kt * 16 + (lane >> 4) * 8;
+    ldmatrix_x4(smem_u32(sQ + att_swz(row, col)), qf[kt][0], qf[kt][1], qf[kt][2], qf[kt][3]);
+  }
+  const int t4 = lane & 3;
+  constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
+  float mx0 = -INFINITY, mx1 = -INFINITY, sum0 = 0.f, sum1 = 0.f;
+  float oacc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int kb = 0; kb < nkb; ++kb) {
+      __syncthreads();                                       // previous tile fully consumed
+      load_tile(sK, 1, kb * ATT_T);
+      if (pass == 1) load_tile(sV, 2, kb * ATT_T);
+      cp_async_wait_all();
+      __syncthreads();
+      float sacc[16][4];
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+          const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int col = kt * 16 + ((lane >> 3) & 1) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(smem_u32(sK + att_swz(key, col)), b0, b1, b2, b3);
+          mma_bf16_16816(sacc[2 * np], qf[kt][0], qf[kt][1], qf[kt][2], qf[kt][3], b0, b1);
+          mma_bf16_16816(sacc[2 * np + 1], qf[kt][0], qf[kt][1], qf[kt][2], qf[kt][3], b2, b3);
+        }
+      }
+      // mask keys >= T (columns 8*nt + 2*t4, +1 of this key block)
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const int k0 = kb * ATT_T + nt * 8 + 2 * t4;
+        if (k0 >= T) { sacc[nt][0] = -INFINITY; sacc[nt][2] = -INFINITY; }
+        if (k0 + 1 >= T) { sacc[nt][1] = -INFINITY; sacc[nt][3] = -INFINITY; }
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+          mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+          sacc[nt][0] = exp2f((sacc[nt][0] - mx0) * kScaleLog2);
+          sacc[nt][1] = exp2f((sacc[nt][1] - mx0) * kScaleLog2);
+          sacc[nt][2] = exp2f((sacc[nt][2] - mx1) * kScaleLog2);
+          sacc[nt][3] = exp2f((sacc[nt][3] - mx1) * kScaleLog2);
+          sum0 += sacc[nt][0] + sacc[nt][1];
+          sum1 += sacc[nt][2] + sacc[nt][3];
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t a0 = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+          const uint32_t a1 = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+          const uint32_t a2 = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+          const uint32_t a3 = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int col = np * 16 + (lane >> 4) * 8;
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(smem_u32(sV + att_swz(key, col)), b0, b1, b2, b3);
+            mma_bf16_16816(oacc[2 * np], a0, a1, a2, a3, b0, b1);
+            mma_bf16_16816(oacc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+          }
+        }
+      }
+    }
+    if (pass == 0) {
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  const int g = lane >> 2;
+  __nv_bfloat16* obase = out + static_cast<long long>(b) * T * D + h * ATT_DH;
+  const int row_lo = q0 + r0 + g, row_hi = row_lo + 8;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * t4;
+    if (row_lo < T) *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_lo) * D + col) = pack_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+    if (row_hi < T) *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_hi) * D + col) = pack_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Decoder context rows for the (position, token) K/V table:
 //   ctx[pos*V + tok] = sqrt(D)*E[tok] + (pos >= 1 ? pos_queries[pos-1] : 0)     (model.py:94-99, modules.py:175-176)
 __global__ void build_ctx_rows_kernel(const float* __restrict__ emb, const float* __restrict__ posq, float* __restrict__ ctx,
@@ -444,7 +575,8 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
   grid_dep_wait();
   const int b = blockIdx.x / qsplit, part = blockIdx.x % qsplit;
   const int q_begin = (part * nq) / qsplit, q_end = ((part + 1) * nq) / qsplit;
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int heads = D >> 5, nwarps = blockDim.x >> 5;   // blockDim.x = min(D, 384): heads are looped when D > 384
   if (threadIdx.x < 32) {
     const int id = (threadIdx.x < nkeys) ? ids[static_cast<long long>(b) * ids_ld + threadIdx.x] : -1;
     s_ids[threadIdx.x] = id;
@@ -453,6 +585,7 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
   }
   __syncthreads();
   const int first_eos = s_first_eos;
+  for (int h = threadIdx.x >> 5; h < heads; h += nwarps) {
   float kreg[32], vreg[32];
   if (lane < nkeys) {
     const uint4* kr = reinterpret_cast<const uint4*>(kvtab + (static_cast<long long>(lane) * V + s_ids[lane]) * 2 * D + h * 32);
@@ -495,6 +628,7 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
     for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, pme, k), vreg[k], acc);
     out[(static_cast<long long>(b) * nq + qi) * D + h * 32 + lane] = __float2bfloat16_rn(acc);
   }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -503,17 +637,19 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
 // pass; the nq queries are distributed over the warps and each query is handled entirely inside one warp (scores
 // for 4 keys per lane, shuffle softmax, lane = channel for P.V): no block-level synchronisation after the load.
 // q fp32 [B*nq, D] pre-scaled by 1/sqrt(32); kv bf16 [B, T, 2D]; out bf16 [B*nq, D].  T <= 128, head dim 32.
+template <int NR>   // keys per lane: T <= 32 * NR (NR = 4: T <= 128, NR = 8: T <= 256)
 __global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __restrict__ q,
                                                               const __nv_bfloat16* __restrict__ kv, int T, int D, int heads,
                                                               int nq, __nv_bfloat16* __restrict__ out) {
-  __shared__ uint32_t sK[128 * 17];                       // bf16x2 words, pitch 17 (odd)
-  __shared__ __align__(16) __nv_bfloat16 sV[128 * 32];
+  constexpr int TK = 32 * NR;
+  __shared__ uint32_t sK[TK * 17];                        // bf16x2 words, pitch 17 (odd)
+  __shared__ __align__(16) __nv_bfloat16 sV[TK * 32];
   grid_dep_launch();
   grid_dep_wait();
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __nv_bfloat16* kvb = kv + static_cast<long long>(b) * T * 2 * D;
-  {
+  for (int t = tid; t < TK; t += 128) {
     uint4* vd = reinterpret_cast<uint4*>(sV + t * 32);
     if (t < T) {
       const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + h * 32);
@@ -536,40 +672,45 @@ __global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __res
   for (int qi = warp; qi < nq; qi += 4) {
     const long long row = static_cast<long long>(b) * nq + qi;
     const float qv = q[row * D + h * 32 + lane];          // lane j holds q_j
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float sc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sc[r] = 0.f;
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
       const float qa = __shfl_sync(0xffffffffu, qv, 2 * w), qb = __shfl_sync(0xffffffffu, qv, 2 * w + 1);
-      const uint32_t k0 = sK[lane * 17 + w], k1 = sK[(32 + lane) * 17 + w], k2 = sK[(64 + lane) * 17 + w],
-                     k3 = sK[(96 + lane) * 17 + w];
-      s0 = fmaf(qb, __uint_as_float(k0 & 0xffff0000u), fmaf(qa, __uint_as_float(k0 << 16), s0));
-      s1 = fmaf(qb, __uint_as_float(k1 & 0xffff0000u), fmaf(qa, __uint_as_float(k1 << 16), s1));
-      s2 = fmaf(qb, __uint_as_float(k2 & 0xffff0000u), fmaf(qa, __uint_as_float(k2 << 16), s2));
-      s3 = fmaf(qb, __uint_as_float(k3 & 0xffff0000u), fmaf(qa, __uint_as_float(k3 << 16), s3));
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const uint32_t kw = sK[(r * 32 + lane) * 17 + w];
+        sc[r] = fmaf(qb, __uint_as_float(kw & 0xffff0000u), fmaf(qa, __uint_as_float(kw << 16), sc[r]));
+      }
     }
-    if (lane >= T) s0 = -INFINITY;
-    if (32 + lane >= T) s1 = -INFINITY;
-    if (64 + lane >= T) s2 = -INFINITY;
-    if (96 + lane >= T) s3 = -INFINITY;
-    float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+    float mx = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      if (r * 32 + lane >= T) sc[r] = -INFINITY;
+      mx = fmaxf(mx, sc[r]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float e0 = expf(s0 - mx), e1 = expf(s1 - mx), e2 = expf(s2 - mx), e3 = expf(s3 - mx);
-    float sum = (e0 + e1) + (e2 + e3);
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      sc[r] = expf(sc[r] - mx);
+      sum += sc[r];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    // P.V with 16-byte smem reads: lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3); 16 iterations cover
-    // the 128 keys; the 8 key groups are then summed with xor-shuffles and lanes 0..3 hold the 32 output channels.
+    // P.V with 16-byte smem reads: lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3); 4*NR iterations cover
+    // the keys; the 8 key groups are then summed with xor-shuffles and lanes 0..3 hold the 32 output channels.
     const int kg = lane >> 2, cc = lane & 3;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.f;
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {                  // key = it*8 + kg -> register e_(it>>2), source lane (it&3)*8 + kg
+    for (int it = 0; it < 4 * NR; ++it) {              // key = it*8 + kg -> register sc[it>>2], source lane (it&3)*8 + kg
       const int key = it * 8 + kg;
       const uint4 vvv = *reinterpret_cast<const uint4*>(sV + key * 32 + cc * 8);
-      const float er = (it >> 2) == 0 ? e0 : (it >> 2) == 1 ? e1 : (it >> 2) == 2 ? e2 : e3;
-      const float pk = __shfl_sync(0xffffffffu, er, (it & 3) * 8 + kg);
+      const float pk = __shfl_sync(0xffffffffu, sc[it >> 2], (it & 3) * 8 + kg);
       const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&vvv);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {

@@ -178,3 +178,23 @@ def test_enc_attention(lib, B, heads, impl):
     err = (out.float() - ref).abs().max().item()
     check(lib, lib.parseq_set_option(None, b"attn_impl", 1))
     assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("B,heads,T", [(2, 6, 196), (3, 12, 240), (1, 3, 130), (2, 6, 64)])
+def test_enc_attention_any_token_count(lib, B, heads, T):
+    """Masked two-pass attention for geometries that do not fill one 128-row tile per image."""
+    from parseq_b200.engine import check
+    d = 64
+    D = heads * d
+    g = torch.Generator(device="cuda").manual_seed(B * 10 + heads + T)
+    qkv = (torch.randn((B * T, 3 * D), device="cuda", generator=g) * 1.5).bfloat16()
+    out = torch.zeros((B * T, D), dtype=torch.bfloat16, device="cuda")
+    check(lib, lib.parseq_enc_attention(qkv.data_ptr(), B, T, D, heads, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().reshape(B, T, 3, heads, d).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * (d ** -0.5)
+    e = torch.exp(s - s.max(-1, keepdim=True).values)
+    o = (e.bfloat16().float() @ v) / e.sum(-1, keepdim=True)
+    ref = o.permute(0, 2, 1, 3).reshape(B * T, D)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err

@@ -206,6 +206,15 @@ def test_full_size_properties_bs512():
     assert torch.isfinite(l1).all()
 
 
+def test_unsupported_geometry_is_rejected_loudly():
+    """More than 256 image tokens is outside what the kernels cover: creation must fail, not fall back."""
+    from parseq_b200.factory import create_model
+    from parseq_b200.engine import EngineError
+    m = create_model("parseq", img_size=[64, 256]).eval().to("cuda")     # 16 x 32 = 512 tokens
+    with pytest.raises(EngineError, match="at most 256 image tokens"):
+        m(torch.zeros(1, 3, 64, 256, device="cuda"))
+
+
 def test_module_api_contract():
     """Surface used by the reference's callers (bench.py:39-46, read.py:37-47, test.py:92-121)."""
     import hubconf
