@@ -293,6 +293,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * B * args.steps / e2e_s
+    # extra: same end-to-end call with raw uint8 HWC crops (transform folded into the patch gather)
+    hu8 = [torch.randint(0, 256, (B, cfg.img_size[0], cfg.img_size[1], 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for i in range(2):
+        eng.forward_u8(hu8[i % 2].data_ptr(), B, hlog.data_ptr(), hids.data_ptr(), hsteps.data_ptr(), st.cuda_stream, None,
+                       True, 1, host=True)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.forward_u8(hu8[i % 2].data_ptr(), B, hlog.data_ptr(), hids.data_ptr(), hsteps.data_ptr(), st.cuda_stream, None,
+                       True, 1, host=True)
+    e2e_u8_s = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e2e_u8_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_u8_s = float(t.item())
+    e2e_u8_val = world * B * args.steps / e2e_u8_s
     h2d = B * 3 * cfg.img_size[0] * cfg.img_size[1] * 4
     d2h = B * 26 * cfg.num_classes * 4 + B * 26 * 4 + 4
 
@@ -373,6 +388,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1000 * e2e_s / args.steps},
+        "e2e_u8": {"value": e2e_u8_val, "unit": "images/s", "h2d_bytes_per_step": h2d // 4, "d2h_bytes_per_step": d2h,
+                   "note": "parseq_forward_host_u8: raw uint8 HWC crops, ToTensor+Normalize folded into the patch gather"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -94,6 +94,21 @@ int parseq_forward_host(parseq_engine* e, const parseq_forward_args* args, const
                         float* logits_host, int32_t* ids_host, int32_t* steps_host,
                         parseq_stream_t stream);
 
+/* "Next" rows of the path.
+ * Raw-crop input: images uint8 [N, H, W, 3] (HWC, as PIL / numpy hold them, already resized to img_size); the reference's
+ * T.ToTensor() + T.Normalize(0.5, 0.5) (strhub/data/module.py:68-82) is folded into the patch gather.  Device / host
+ * variants mirror parseq_forward / parseq_forward_host. */
+int parseq_forward_u8(parseq_engine* e, const parseq_forward_args* args, const uint8_t* images_hwc,
+                      float* logits, int32_t* ids, int32_t* steps, parseq_stream_t stream);
+int parseq_forward_host_u8(parseq_engine* e, const parseq_forward_args* args, const uint8_t* images_hwc_host,
+                           float* logits_host, int32_t* ids_host, int32_t* steps_host, parseq_stream_t stream);
+/* Fused post-processing of BaseSystem._eval_step (strhub/models/base.py:132-142) + Tokenizer._filter
+ * (strhub/data/utils.py:120-129): DEVICE logits [N, num_steps, num_classes] -> ids [N, num_steps] (greedy), lengths [N]
+ * (index of the first EOS, num_steps if none) and confidence [N] (product of the max softmax probabilities up to and
+ * including the EOS position). */
+int parseq_postprocess(const float* logits, int32_t batch, int32_t num_steps, int32_t num_classes, int32_t eos_id,
+                       int32_t* ids, int32_t* lengths, float* confidence, parseq_stream_t stream);
+
 /* Replaces model.PARSeq.encode (model.py:83-84): memory DEVICE fp32 [N, T, D]. */
 int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* memory,
                   parseq_stream_t stream);

@@ -336,6 +336,7 @@ struct parseq_engine {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // static I/O buffers the CUDA graphs are captured on
   float* in_images = nullptr; float* out_logits = nullptr; int* out_ids = nullptr; int* out_steps = nullptr;
+  uint8_t* in_images_u8 = nullptr;  // static input of the uint8 HWC entry points
   bool use_graph = true;
   struct GraphEntry { cudaGraphExec_t exec; long long kernels; };
   std::map<std::vector<int>, GraphEntry> graphs;
@@ -398,6 +399,7 @@ int alloc_workspace(parseq_engine* e) {
   }
   const long long NB = e->max_batch;
   PQ_TRY(dev_alloc(&e->in_images, NB * 3 * e->cfg.img_h * e->cfg.img_w));
+  PQ_TRY(dev_alloc(&e->in_images_u8, NB * 3 * e->cfg.img_h * e->cfg.img_w));
   PQ_TRY(dev_alloc(&e->out_logits, NB * e->L * e->C));
   PQ_TRY(dev_alloc(&e->out_ids, NB * e->L));
   PQ_TRY(dev_alloc(&e->out_steps, 4));
@@ -412,8 +414,8 @@ void drop_graphs(parseq_engine* e) {
 void free_workspace(parseq_engine* e) {
   drop_graphs(e);
   void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->mem, e->ckv, e->in_images, e->out_logits, e->out_ids,
-                  e->out_steps, e->ar_sa, e->ar_ca, e->ar_hd, e->ar_y, e->ar_qc, e->ar_part, e->ar_ids, e->ar_bar, e->ar_prof};
-  e->ar_part = nullptr; e->ar_prof = nullptr;
+                  e->out_steps, e->in_images_u8, e->ar_sa, e->ar_ca, e->ar_hd, e->ar_y, e->ar_qc, e->ar_part, e->ar_ids, e->ar_bar, e->ar_prof};
+  e->ar_part = nullptr; e->ar_prof = nullptr; e->in_images_u8 = nullptr;
   e->ar_sa = e->ar_ca = e->ar_hd = nullptr; e->ar_y = e->ar_qc = nullptr; e->ar_ids = nullptr; e->ar_bar = nullptr;
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -465,16 +467,23 @@ int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float
 }
 
 // ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
-int encode_chunk(parseq_engine* e, const float* images, int B, __nv_bfloat16* mem_out, float* memory32,
+int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_bfloat16* mem_out, float* memory32,
                  cudaStream_t st) {
   const int D = e->D, T = e->T, M = B * T;
   e->cur_cat = CAT_ENC_GEMM;
   {
     TimedScope ts(e, st, CAT_MISC, 0.0);
-    const long long total = static_cast<long long>(B) * e->gh * e->gw * 3 * e->cfg.patch_h;
-    const int grid = static_cast<int>((total + 255) / 256);
-    PQ_TRY(launch_k(pq::im2col_patch_kernel, dim3(grid), dim3(256), 0, st, images, e->a_pe, B, e->cfg.img_h, e->cfg.img_w,
-                    e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
+    if (u8) {
+      const long long total = static_cast<long long>(B) * e->gh * e->gw * e->cfg.patch_h;
+      const int grid = static_cast<int>((total + 255) / 256);
+      PQ_TRY(launch_k(pq::im2col_patch_u8_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(images_any), e->a_pe,
+                      B, e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
+    } else {
+      const long long total = static_cast<long long>(B) * e->gh * e->gw * 3 * e->cfg.patch_h;
+      const int grid = static_cast<int>((total + 255) / 256);
+      PQ_TRY(launch_k(pq::im2col_patch_kernel, dim3(grid), dim3(256), 0, st, static_cast<const float*>(images_any), e->a_pe, B,
+                      e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
+    }
   }
   // x = patches * Wpe^T + bpe + pos_embed
   PQ_TRY(gemm(e, e->a_pe, e->Kp, e->w("encoder.patch_embed.proj.weight"), e->Kp,
@@ -668,13 +677,13 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
 // One super-chunk (B <= max_batch images): `main` encodes everything (in `chunk`-image pieces) and projects the cross
 // K/V of the whole super-chunk; then the decoder - a latency-bound chain of small kernels - runs as ceil(B/dec_chunk)
 // independent chains on their own streams, concurrently (event fork/join, capturable into a CUDA graph).
-int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const float* images,
+int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const void* images, bool u8,
                   float* logits, int* ids_out, int* steps) {
-  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w * (u8 ? 1 : 4);   // bytes per image
   const int D = e->D, T = e->T;
   for (int o = 0; o < B; o += e->chunk) {
     const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
-    PQ_TRY(encode_chunk(e, images + o * img_sz, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
+    PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
   }
   // cross-attention K/V of the image memory, once per image (the reference recomputes it in every decode call)
   e->cur_cat = CAT_DEC_GEMM;
@@ -717,8 +726,8 @@ int num_steps_of(const parseq_engine* e, int max_length) {
 }
 
 // Replays (capturing on first use) the CUDA graph of one super-chunk of Bc images on the static I/O buffers.
-int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L) {
-  std::vector<int> key = {Bc, L, a->max_length < 0 ? 1 : 0, a->decode_ar ? 1 : 0, a->refine_iters};
+int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L, bool u8) {
+  std::vector<int> key = {Bc, L, a->max_length < 0 ? 1 : 0, a->decode_ar ? 1 : 0, a->refine_iters, u8 ? 1 : 0};
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     parseq_forward_args aa = *a;
@@ -727,7 +736,8 @@ int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L) {
     aa.forced_refine = nullptr;
     const long long before = e->launches;
     PQ_CUDA(cudaStreamBeginCapture(e->main, cudaStreamCaptureModeThreadLocal));
-    int r = forward_super(e, &aa, 0, Bc, L, e->in_images, e->out_logits, e->out_ids, e->out_steps);
+    int r = forward_super(e, &aa, 0, Bc, L, u8 ? static_cast<const void*>(e->in_images_u8) : static_cast<const void*>(e->in_images),
+                          u8, e->out_logits, e->out_ids, e->out_steps);
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->main, &g);
     if (r != PARSEQ_OK) { if (g) cudaGraphDestroy(g); return r; }
@@ -746,11 +756,13 @@ int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L) {
 }
 
 // Common driver of parseq_forward / parseq_forward_host. `host` selects H2D/D2H vs D2D staging copies.
-int forward_impl(parseq_engine* e, const parseq_forward_args* a, const float* images, float* logits, int32_t* ids,
-                 int32_t* steps, cudaStream_t user, bool host) {
+int forward_impl(parseq_engine* e, const parseq_forward_args* a, const void* images_any, float* logits, int32_t* ids,
+                 int32_t* steps, cudaStream_t user, bool host, bool u8 = false) {
   const int L = num_steps_of(e, a->max_length);
   const bool testing = a->max_length < 0;
-  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
+  const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w * (u8 ? 1 : 4);   // bytes per image
+  const char* images = static_cast<const char*>(images_any);
+  void* in_static = u8 ? static_cast<void*>(e->in_images_u8) : static_cast<void*>(e->in_images);
   const bool eager = !e->use_graph || e->timing || a->forced_ids != nullptr || a->forced_refine != nullptr;
   const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
@@ -762,15 +774,15 @@ int forward_impl(parseq_engine* e, const parseq_forward_args* a, const float* im
   for (int b0 = 0; b0 < a->batch; b0 += e->max_batch) {
     const int Bc = (a->batch - b0 < e->max_batch) ? (a->batch - b0) : e->max_batch;
     if (eager && !host) {
-      PQ_TRY(forward_super(e, a, b0, Bc, L, images + b0 * img_sz, logits + 1ll * b0 * L * e->C,
+      PQ_TRY(forward_super(e, a, b0, Bc, L, images + b0 * img_sz, u8, logits + 1ll * b0 * L * e->C,
                            ids ? ids + 1ll * b0 * L : nullptr, e->out_steps));
       continue;
     }
-    PQ_CUDA(cudaMemcpyAsync(e->in_images, images + b0 * img_sz, static_cast<size_t>(Bc * img_sz) * 4, kin, e->main));
+    PQ_CUDA(cudaMemcpyAsync(in_static, images + b0 * img_sz, static_cast<size_t>(Bc * img_sz), kin, e->main));
     if (eager) {
-      PQ_TRY(forward_super(e, a, b0, Bc, L, e->in_images, e->out_logits, e->out_ids, e->out_steps));
+      PQ_TRY(forward_super(e, a, b0, Bc, L, in_static, u8, e->out_logits, e->out_ids, e->out_steps));
     } else {
-      PQ_TRY(run_graph(e, a, Bc, L));
+      PQ_TRY(run_graph(e, a, Bc, L, u8));
     }
     PQ_CUDA(cudaMemcpyAsync(logits + 1ll * b0 * L * e->C, e->out_logits, static_cast<size_t>(1ll * Bc * L * e->C) * 4, kout,
                             e->main));
@@ -1012,6 +1024,43 @@ int parseq_forward_host(parseq_engine* e, const parseq_forward_args* a, const fl
   return PARSEQ_OK;
 }
 
+int parseq_forward_u8(parseq_engine* e, const parseq_forward_args* a, const uint8_t* images_hwc, float* logits, int32_t* ids,
+                      int32_t* steps, parseq_stream_t stream) {
+  if (e == nullptr || a == nullptr || images_hwc == nullptr || logits == nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
+  if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
+  if (a->batch == 0) return PARSEQ_OK;
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  return forward_impl(e, a, images_hwc, logits, ids, steps, reinterpret_cast<cudaStream_t>(stream), false, true);
+}
+
+int parseq_forward_host_u8(parseq_engine* e, const parseq_forward_args* a, const uint8_t* images_hwc_host, float* logits_host,
+                           int32_t* ids_host, int32_t* steps_host, parseq_stream_t stream) {
+  if (e == nullptr || a == nullptr || images_hwc_host == nullptr || logits_host == nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
+  if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
+  if (a->batch == 0) return PARSEQ_OK;
+  if (a->forced_ids != nullptr || a->forced_refine != nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "teacher forcing is a device-pointer API (parseq_forward)");
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  PQ_TRY(forward_impl(e, a, images_hwc_host, logits_host, ids_host, steps_host, reinterpret_cast<cudaStream_t>(stream), true, true));
+  PQ_CUDA(cudaStreamSynchronize(e->main));
+  return PARSEQ_OK;
+}
+
+int parseq_postprocess(const float* logits, int32_t batch, int32_t num_steps, int32_t num_classes, int32_t eos_id, int32_t* ids,
+                       int32_t* lengths, float* confidence, parseq_stream_t stream) {
+  if (logits == nullptr || ids == nullptr || lengths == nullptr || confidence == nullptr)
+    return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (batch <= 0) return batch == 0 ? PARSEQ_OK : fail(PARSEQ_ERR_INVALID_ARG, "negative batch");
+  pq::postprocess_kernel<<<(batch + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, batch, num_steps, num_classes,
+                                                                                              eos_id, ids, lengths, confidence);
+  PQ_CUDA(cudaGetLastError());
+  return PARSEQ_OK;
+}
+
 int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* memory, parseq_stream_t stream) {
   if (e == nullptr || images == nullptr || memory == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called");
@@ -1022,7 +1071,7 @@ int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* m
   const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w;
   for (int b0 = 0; b0 < batch; b0 += e->chunk) {
     const int B = (batch - b0 < e->chunk) ? (batch - b0) : e->chunk;
-    PQ_TRY(encode_chunk(e, images + b0 * img_sz, B, e->mem, memory + 1ll * b0 * e->T * e->D, e->main));
+    PQ_TRY(encode_chunk(e, images + b0 * img_sz, false, B, e->mem, memory + 1ll * b0 * e->T * e->D, e->main));
   }
   PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
   PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));

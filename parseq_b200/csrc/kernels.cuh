@@ -40,6 +40,34 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16
   }
 }
 
+// Same gather for raw uint8 HWC crops [B, H, W, 3] with the reference's input transform folded in:
+// T.ToTensor() (u / 255) followed by T.Normalize(0.5, 0.5) ((x - 0.5) / 0.5)  (strhub/data/module.py:68-82), evaluated in
+// fp32 with IEEE division exactly like torchvision, then rounded to bf16 like the float path.
+__global__ void im2col_patch_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
+                                       int W, int ph, int pw, int gh, int gw) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long total = static_cast<long long>(B) * gh * gw * ph;     // one thread per (token, dy): pw*3 bytes
+  const int Kp = 3 * ph * pw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = i;
+    const int c = static_cast<int>(t % gw); t /= gw;
+    const int dy = static_cast<int>(t % ph); t /= ph;
+    const int r = static_cast<int>(t % gh); t /= gh;
+    const int b = static_cast<int>(t);
+    const uint8_t* src = img + ((static_cast<long long>(b) * H + (r * ph + dy)) * W + c * pw) * 3;
+    __nv_bfloat16* dst = out + (static_cast<long long>(b) * gh * gw + r * gw + c) * Kp + dy * pw;
+    for (int dx = 0; dx < pw; ++dx) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float x = __fdiv_rn(static_cast<float>(src[dx * 3 + ch]), 255.0f);
+        dst[ch * ph * pw + dx] = __float2bfloat16_rn(__fdiv_rn(x - 0.5f, 0.5f));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (biased variance, two-pass in registers), one warp per row.
 // y_bf16 = bf16(LN(x)); optional fp32 copy (encoder output `memory`).
@@ -867,6 +895,49 @@ __global__ void __launch_bounds__(384) dec_ln_head_argmax_kernel(
         ids[static_cast<long long>(b) * ids_ld + dst_off + qi] = v;
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused post-processing of the reference's test path (strhub/models/base.py:132-142 + Tokenizer._filter,
+// strhub/data/utils.py:120-129): per image  ids[i] = argmax_c logits[i, c]  (first maximum),  length = index of the
+// first EOS (L if none),  confidence = prod_{i <= min(length, L-1)} max_c softmax(logits[i])_c  (the EOS probability is
+// included).  One warp per image; only (length, confidence, ids) cross PCIe instead of the [B, L, C] probabilities.
+__global__ void postprocess_kernel(const float* __restrict__ logits, int B, int L, int C, int eos_id, int* __restrict__ ids,
+                                   int* __restrict__ lengths, float* __restrict__ confidence) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  float conf = 1.0f;
+  int len = L;
+  bool done = false;
+  for (int i = 0; i < L; ++i) {
+    const float* row = logits + (static_cast<long long>(b) * L + i) * C;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < C; j += 32) {
+      const float v = row[j];
+      if (v > best) { best = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    float se = 0.f;
+    for (int j = lane; j < C; j += 32) se += expf(row[j] - best);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (lane == 0) ids[static_cast<long long>(b) * L + i] = bi;
+    if (!done) {
+      conf *= 1.0f / se;                 // max softmax probability of position i
+      if (bi == eos_id) { len = i; done = true; }
+    }
+  }
+  if (lane == 0) {
+    lengths[b] = len;
+    confidence[b] = conf;
   }
 }
 

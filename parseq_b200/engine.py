@@ -25,7 +25,8 @@ class ForwardArgsC(C.Structure):
 
 EXPORTS = [
     "parseq_create", "parseq_destroy", "parseq_set_weight", "parseq_num_weights", "parseq_weight_key",
-    "parseq_finalize", "parseq_forward", "parseq_forward_host", "parseq_encode", "parseq_kernel_launches",
+    "parseq_finalize", "parseq_forward", "parseq_forward_host", "parseq_forward_u8", "parseq_forward_host_u8",
+    "parseq_postprocess", "parseq_encode", "parseq_kernel_launches",
     "parseq_set_option", "parseq_get_timing", "parseq_get_ar_profile", "parseq_last_error", "parseq_version", "parseq_gemm_bf16", "parseq_layernorm_bf16",
     "parseq_enc_attention",
 ]
@@ -55,6 +56,10 @@ def load_library(path: Optional[str] = None):
     lib.parseq_forward.argtypes = [C.c_void_p, C.POINTER(ForwardArgsC), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
     lib.parseq_forward_host.argtypes = lib.parseq_forward.argtypes
+    lib.parseq_forward_u8.argtypes = lib.parseq_forward.argtypes
+    lib.parseq_forward_host_u8.argtypes = lib.parseq_forward.argtypes
+    lib.parseq_postprocess.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
     lib.parseq_encode.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.parseq_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.parseq_get_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -169,6 +174,16 @@ class Engine:
         a = self._args(batch, max_length, decode_ar, refine_iters)
         check(self.lib, self.lib.parseq_forward_host(self.handle, C.byref(a), images_ptr, logits_ptr, ids_ptr,
                                                      steps_ptr, stream))
+
+    def forward_u8(self, images_ptr, batch, logits_ptr, ids_ptr, steps_ptr, stream, max_length=None, decode_ar=True,
+                   refine_iters=1, host=False):
+        a = self._args(batch, max_length, decode_ar, refine_iters)
+        fn = self.lib.parseq_forward_host_u8 if host else self.lib.parseq_forward_u8
+        check(self.lib, fn(self.handle, C.byref(a), images_ptr, logits_ptr, ids_ptr, steps_ptr, stream))
+
+    def postprocess(self, logits_ptr, batch, num_steps, ids_ptr, lengths_ptr, conf_ptr, stream, eos_id=0):
+        check(self.lib, self.lib.parseq_postprocess(logits_ptr, batch, num_steps, self.cfg.num_classes, eos_id, ids_ptr,
+                                                    lengths_ptr, conf_ptr, stream))
 
     def encode(self, images_ptr, batch, memory_ptr, stream):
         check(self.lib, self.lib.parseq_encode(self.handle, batch, images_ptr, memory_ptr, stream))

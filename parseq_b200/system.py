@@ -118,6 +118,10 @@ class ParseqModel(nn.Module):
         if images.device.type != "cuda":
             raise RuntimeError("images must be CUDA tensors (no CPU fallback)")
         H, W = self.cfg.img_size
+        if images.dtype == torch.uint8:      # raw crops [N, H, W, 3]: ToTensor + Normalize(0.5, 0.5) run inside the engine
+            if images.dim() != 4 or tuple(images.shape[1:]) != (H, W, 3):
+                raise AssertionError(f"uint8 input must be (N,{H},{W},3), got {tuple(images.shape)}")
+            return images.contiguous()
         if images.dim() != 4 or images.shape[1] != 3 or tuple(images.shape[-2:]) != (H, W):
             raise AssertionError(f"Input image size {tuple(images.shape)} doesn't match model (N,3,{H},{W})")
         return images.to(torch.float32).contiguous()
@@ -149,9 +153,13 @@ class ParseqModel(nn.Module):
         steps = torch.empty((1,), dtype=torch.int32, device=dev)
         fi = forced_ids.to(device=dev, dtype=torch.int32).contiguous() if forced_ids is not None else None
         fr = forced_refine.to(device=dev, dtype=torch.int32).contiguous() if forced_refine is not None else None
-        eng.forward(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(),
-                    torch.cuda.current_stream(dev).cuda_stream, max_length, self.decode_ar, self.refine_iters,
-                    fi.data_ptr() if fi is not None else None, fr.data_ptr() if fr is not None else None)
+        if images.dtype == torch.uint8:
+            eng.forward_u8(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(),
+                           torch.cuda.current_stream(dev).cuda_stream, max_length, self.decode_ar, self.refine_iters)
+        else:
+            eng.forward(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(),
+                        torch.cuda.current_stream(dev).cuda_stream, max_length, self.decode_ar, self.refine_iters,
+                        fi.data_ptr() if fi is not None else None, fr.data_ptr() if fr is not None else None)
         if max_length is None and self.decode_ar and not self.refine_iters:
             # model.py:144-147: with no refinement the reference returns only the S steps it ran
             S = int(steps.item())
@@ -212,16 +220,31 @@ class PARSeq(nn.Module):
     def forward(self, images: Tensor, max_length: Optional[int] = None) -> Tensor:
         return self.model.forward(self.tokenizer, images, max_length)
 
+    def postprocess(self, logits: Tensor):
+        """Device-side greedy decode of logits [N, L, C]: (labels, confidences) with the semantics of
+        `logits.softmax(-1)` -> `tokenizer.decode` -> `prob.prod()` (base.py:132-142); one small D2H per batch."""
+        eng = self.model.engine()
+        logits = logits.contiguous()
+        N, L, _ = logits.shape
+        dev = logits.device
+        ids = torch.empty((N, L), dtype=torch.int32, device=dev)
+        lengths = torch.empty((N,), dtype=torch.int32, device=dev)
+        conf = torch.empty((N,), dtype=torch.float32, device=dev)
+        eng.postprocess(logits.data_ptr(), N, L, ids.data_ptr(), lengths.data_ptr(), conf.data_ptr(),
+                        torch.cuda.current_stream(dev).cuda_stream, self.eos_id)
+        ids_h, len_h, conf_h = ids.cpu().tolist(), lengths.cpu().tolist(), conf.cpu().tolist()
+        labels = [self.tokenizer._ids2tok(row[:n], True) for row, n in zip(ids_h, len_h)]
+        return labels, conf_h
+
     # base.py:112-143,179-180 (test path only; validation loss is a training concern)
     def _eval_step(self, batch, validation: bool = False):
         images, labels = batch
         logits = self.forward(images)
-        probs = logits.softmax(-1)
-        preds, probs = self.tokenizer.decode(probs)
+        preds, confs = self.postprocess(logits)
         correct = total = label_length = 0
         ned = confidence = 0.0
-        for pred, prob, gt in zip(preds, probs, labels):
-            confidence += prob.prod().item()
+        for pred, conf_i, gt in zip(preds, confs, labels):
+            confidence += conf_i
             pred = self.charset_adapter(pred)
             ned += edit_distance(pred, gt) / max(len(pred), len(gt), 1)
             correct += int(pred == gt)

@@ -206,6 +206,36 @@ def test_full_size_properties_bs512():
     assert torch.isfinite(l1).all()
 
 
+def test_uint8_input_path_is_bit_identical_to_float_path():
+    """raw uint8 HWC crops with ToTensor + Normalize(0.5, 0.5) folded into the patch gather give exactly
+    the logits of the float path fed with torchvision's transform of the same pixels (module.py:68-82)."""
+    cfg, sd, m = _model("parseq", 0)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (5, 32, 128, 3), dtype=torch.uint8, generator=g)
+    xf = (u8.permute(0, 3, 1, 2).to(torch.float32).div(255) - 0.5) / 0.5          # ToTensor, Normalize(0.5, 0.5)
+    with torch.inference_mode():
+        lf = m(xf.cuda())
+        lu = m(u8.cuda())
+    assert torch.equal(lf, lu)
+
+
+def test_fused_postprocess_matches_reference_semantics():
+    """ids / lengths / confidence on device == softmax -> Tokenizer.decode -> prob.prod() (base.py:132-142)."""
+    cfg, sd, m = _model("parseq", 1, eos_bias=0.5)
+    from parseq_b200.weights import synth_images
+    x = synth_images(cfg, 16, 9).cuda()
+    with torch.inference_mode():
+        logits = m(x)
+        labels, confs = m.postprocess(logits)
+        ref_labels, ref_probs = m.tokenizer.decode(logits.softmax(-1))
+    assert labels == ref_labels
+    ref_conf = [p.prod().item() for p in ref_probs]
+    assert max(abs(a - b) for a, b in zip(confs, ref_conf)) <= 1e-5 * max(1e-30, max(ref_conf)) + 1e-7
+    assert any(len(l) < 26 for l in labels)          # the EOS-biased weights do truncate some labels
+    res = m.test_step((x, ["x"] * 16), -1)["output"]
+    assert res.num_samples == 16 and abs(res.confidence - sum(ref_conf)) < 1e-4
+
+
 def test_unsupported_geometry_is_rejected_loudly():
     """More than 256 image tokens is outside what the kernels cover: creation must fail, not fall back."""
     from parseq_b200.factory import create_model
