@@ -45,9 +45,15 @@ typedef struct parseq_config {
   int32_t num_tokens;                    /* 97: EOS=0, chars 1..94, BOS=95, PAD=96 (data/utils.py:102-111) */
   int32_t max_batch;                     /* images per super-chunk / CUDA graph (workspace sizing); 0 = 512 */
   int32_t device;                        /* CUDA device ordinal */
+  int32_t arch;                          /* 0: PARSeq (parseq/model.py); 1: ViTSTR (vitstr/model.py:14-28: the same ViT with
+                                          * a class token and a per-token head; the dec_* fields are ignored) */
 } parseq_config;
 
-/* Replaces model.PARSeq.__init__ (model.py:33-71): allocates device weights + workspace. */
+/* Replaces model.PARSeq.__init__ (model.py:33-71): allocates device weights + workspace.
+ * arch = 1 replaces vitstr/system.py:50-59 (ViTSTR(VisionTransformer) ctor): state_dict keys are then those of the
+ * timm ViT itself ("cls_token", "pos_embed" [1, T+1, D], "patch_embed.proj.*", "blocks.<i>.*", "norm.*", "head.*");
+ * parseq_forward* ignore decode_ar / refine_iters and return vitstr/system.py:65-71: head(norm(x))[:, 1 : max_length+2]
+ * as logits [N, num_steps, num_tokens-2]; parseq_encode returns forward_features [N, T+1, D]. */
 int parseq_create(const parseq_config* cfg, parseq_engine** out);
 void parseq_destroy(parseq_engine* e);
 

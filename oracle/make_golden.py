@@ -120,8 +120,46 @@ def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau):
     torch.save(blob, os.path.join(OUT, name + ".pt"))
 
 
+# (case name, config overrides, weight seed, batch, image seed, max_length)
+VITSTR_CASES = [
+    ("vitstr_s_b3",      dict(), 20, 3, 30, None),
+    ("vitstr_s_len5_b2", dict(), 20, 2, 31, 5),
+    ("vitstr_s_len0_b1", dict(), 20, 1, 32, 0),
+    # configs/model/vitstr.yaml geometry (224x224 / 16x16: 196 patches + class token)
+    ("vitstr_p16_b1",    dict(img_size=(224, 224), patch_size=(16, 16)), 21, 1, 33, None),
+]
+
+
+def make_vitstr():
+    """Golden outputs of the reference's own `strhub.models.vitstr.model.ViTSTR` (under the timm shim) with the call and
+    slice of vitstr/system.py:65-71."""
+    from oracle.vitstr_oracle import VitstrOracle
+    os.makedirs(OUT, exist_ok=True)
+    for name, over, wseed, B, iseed, ml in VITSTR_CASES:
+        cfg = make_config("vitstr", **over)
+        sd = init_state_dict(cfg, wseed)
+        ref = RL.build_reference_vitstr(cfg, sd)
+        x = synth_images(cfg, B, iseed)
+        m = cfg.max_label_length if ml is None else min(ml, cfg.max_label_length)
+        with torch.inference_mode():
+            logits = ref(x, m + 2)[:, 1:].clone()               # vitstr/system.py:67-70
+            feats = ref.forward_features(x).clone()
+        o = VitstrOracle(cfg, sd, "fp64")
+        err = (o.system_forward(x, ml).float() - logits).abs().max().item()
+        assert err < 1e-5, (name, err)
+        blob = dict(name=name, experiment="vitstr", overrides=over, weight_seed=wseed, batch=B, image_seed=iseed,
+                    max_length=ml, sd_digest=state_dict_digest(sd), logits=logits.contiguous(),
+                    features0=feats[0].contiguous(),
+                    source="reference strhub.models.vitstr.model.ViTSTR @ /root/reference (timm shim), torch %s CPU fp32"
+                           % torch.__version__)
+        torch.save(blob, os.path.join(OUT, name + ".pt"))
+        print(f"{name:18s} logits {tuple(logits.shape)} |ref-fp64 oracle|={err:.2e}")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "filtered_ti":
+    if len(sys.argv) > 1 and sys.argv[1] == "vitstr":
+        make_vitstr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "filtered_ti":
         make_filtered("filtered_ti_ar1_len5", "parseq-tiny", 2, True, 1, 5, 4, 256, 0.012)
     elif len(sys.argv) > 1 and sys.argv[1] == "filtered":
         make_filtered("filtered_s_ar1", "parseq", 0, True, 1, None, 16, 256, 0.02)

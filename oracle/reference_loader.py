@@ -42,6 +42,43 @@ def load_reference_classes():
     return Ref, Tok
 
 
+def load_reference_vitstr_class():
+    """The reference's inner `strhub.models.vitstr.model.ViTSTR` (a timm VisionTransformer subclass; under the shim).
+    The Lightning system around it (vitstr/system.py) needs pytorch_lightning / nltk and is restated by
+    oracle/vitstr_oracle.py:system_forward instead."""
+    from . import timm_shim
+    timm_shim.install()
+    saved = {k: v for k, v in sys.modules.items() if k == "strhub" or k.startswith("strhub.")}
+    for k in saved:
+        del sys.modules[k]
+    import types
+    sys.path.insert(0, REF_ROOT)
+    try:
+        # bypass strhub/models/vitstr/__init__ -> system.py (pytorch_lightning): load model.py as a plain module
+        for pkg in ("strhub", "strhub.models", "strhub.models.vitstr"):
+            m = types.ModuleType(pkg)
+            m.__path__ = [os.path.join(REF_ROOT, *pkg.split("."))]
+            sys.modules[pkg] = m
+        mod = importlib.import_module("strhub.models.vitstr.model")
+        assert os.path.realpath(mod.__file__).startswith(os.path.realpath(REF_ROOT)), mod.__file__
+        cls = mod.ViTSTR
+    finally:
+        sys.path.remove(REF_ROOT)
+        for k in [k for k in sys.modules if k == "strhub" or k.startswith("strhub.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return cls
+
+
+def build_reference_vitstr(cfg, state_dict):
+    """ctor arguments of vitstr/system.py:50-59."""
+    cls = load_reference_vitstr_class()
+    m = cls(img_size=list(cfg.img_size), patch_size=list(cfg.patch_size), depth=cfg.enc_depth, mlp_ratio=cfg.enc_mlp_ratio,
+            qkv_bias=True, embed_dim=cfg.embed_dim, num_heads=cfg.enc_num_heads, num_classes=cfg.num_classes)
+    m.load_state_dict(state_dict, strict=True)
+    return m.eval()
+
+
 def build_reference_model(cfg, state_dict):
     Ref, Tok = load_reference_classes()
     tok = Tok(cfg.charset_train)

@@ -8,7 +8,9 @@ The reference touches: `timm.models.vision_transformer.{VisionTransformer, Patch
 (modules.py:24) and `timm.models.helpers.named_apply` (model.py:23).  This file restates the
 timm-0.9.16 ViT forward for exactly the constructor arguments the reference passes
 (modules.py:145-161: num_classes=0, global_pool='', class_token=False, qkv_bias=True, all drop
-rates 0) with timm's parameter names, so `state_dict()` keys match released PARSeq weights.
+rates 0) with timm's parameter names, so `state_dict()` keys match released PARSeq weights, and
+for the ctor of strhub/models/vitstr/system.py:50-59 (timm defaults class_token=True,
+global_pool='token', num_classes=len(tokenizer)-2: `cls_token`, `pos_embed` [1, T+1, D], `head`).
 It is my own restatement of published semantics, not timm code => encoder "parity unpinned".
 """
 from __future__ import annotations
@@ -82,15 +84,22 @@ class VisionTransformer(nn.Module):
                  embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0, qkv_bias=True, class_token=True,
                  drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, embed_layer=PatchEmbed, **_):
         super().__init__()
-        assert num_classes == 0 and global_pool == '' and not class_token, "shim covers the PARSeq ctor only"
+        assert (num_classes == 0 and global_pool == '' and not class_token) or \
+               (num_classes > 0 and global_pool == 'token' and class_token), "shim covers the PARSeq and ViTSTR ctors only"
         assert drop_rate == attn_drop_rate == drop_path_rate == 0.0
         self.embed_dim = embed_dim
+        self.num_classes = num_classes
         self.patch_embed = embed_layer(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
                                        embed_dim=embed_dim)
-        self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches, embed_dim))
+        # timm 0.9.16 VisionTransformer.__init__: cls_token [1,1,D]; pos_embed covers the prefix token too
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim)) if class_token else None
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + (1 if class_token else 0), embed_dim))
         self.blocks = nn.Sequential(*[_Block(embed_dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
         self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head = nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity()
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        if self.cls_token is not None:
+            nn.init.normal_(self.cls_token, std=1e-6)
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.trunc_normal_(m.weight, std=0.02)
@@ -98,14 +107,20 @@ class VisionTransformer(nn.Module):
                     nn.init.zeros_(m.bias)
 
     def no_weight_decay(self):
-        return {'pos_embed'}
+        return {'pos_embed', 'cls_token'}
 
     def forward_features(self, x):
-        x = self.patch_embed(x) + self.pos_embed
+        x = self.patch_embed(x)
+        if self.cls_token is not None:       # timm _pos_embed (no_embed_class=False): concat, then add
+            x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1)
+        x = x + self.pos_embed
         return self.norm(self.blocks(x))
 
     def forward(self, x):
-        return self.forward_features(x)
+        x = self.forward_features(x)
+        if self.num_classes > 0:             # global_pool='token'
+            return self.head(x[:, 0])
+        return x
 
 
 def named_apply(fn, module, name='', depth_first=True, include_root=False):

@@ -47,6 +47,10 @@ class ParseqConfig:
     perm_mirrored: bool = True
     dropout: float = 0.1
     name: str = "parseq"
+    # "parseq" | "vitstr" (strhub/models/vitstr: the same ViT with a class token + per-token head, no decoder;
+    # embed_dim / enc_num_heads carry ViTSTR's embed_dim / num_heads, depth 12 and mlp_ratio 4 are fixed by
+    # vitstr/system.py:50-59)
+    arch: str = "parseq"
     extra: Dict[str, Any] = field(default_factory=dict)
 
     # ---- derived ----
@@ -66,6 +70,10 @@ class ParseqConfig:
     def num_patches(self) -> int:
         g = self.grid
         return g[0] * g[1]
+
+    @property
+    def enc_tokens(self) -> int:          # tokens per image inside the encoder (ViTSTR keeps timm's class token)
+        return self.num_patches + (1 if self.arch == "vitstr" else 0)
 
     @property
     def patch_dim(self) -> int:
@@ -94,6 +102,8 @@ PRESETS: Dict[str, Dict[str, Any]] = {
     "parseq-patch16-224": dict(name="parseq-patch16-224", img_size=(224, 224), patch_size=(16, 16)),
     # BASELINE.json configs[4]: ViT-B-width encoder stress config (not a reference experiment;
     # heads follow the D/64 (enc) and D/32 (dec) convention of the S / Ti configs)
+    # configs/model/vitstr.yaml + configs/experiment/vitstr.yaml (32x128 crops, 4x8 patches, ViT-S width)
+    "vitstr": dict(name="vitstr", arch="vitstr", lr=8.9e-4),
     "parseq-base-48x160": dict(name="parseq-base-48x160", embed_dim=768, enc_num_heads=12,
                                dec_num_heads=24, img_size=(48, 160)),
 }

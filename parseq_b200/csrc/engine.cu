@@ -106,6 +106,7 @@ int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
 int g_block_n_override = 0;
 int g_cta_group_override = 0;   // 0 = auto, 1 / 2 = forced (tests)
 bool g_no_tma_epilogue = false; // tests: force the direct-store epilogue
+int g_gemm_stages = 0;          // experiments: cap the operand ring depth (0 = full)
 
 template <int BN, int CG>
 int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const pq::GemmParams& p, int tiles,
@@ -231,6 +232,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
   else if (p.tma_out != 0) PQ_TRY(make_tmap(&tc, out, 4, M, N, ldo, 32, 32));
   else tc = ta;
   const int tile_m = pq::GEMM_BLOCK_M * CG;
+  p.max_stages = g_gemm_stages;
   p.num_m_tiles = (M + tile_m - 1) / tile_m;
   p.num_n_tiles = (N + BN - 1) / BN;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -282,7 +284,8 @@ int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* 
 }
 
 struct Slot {
-  std::string key;
+  std::string key;   // internal name (PARSeq state_dict key)
+  std::string pub;   // state_dict key of the served architecture (== key for PARSeq; ViTSTR drops the "encoder." prefix)
   long long numel;
   bool bf16;
   void* dev;
@@ -293,7 +296,10 @@ struct Slot {
 
 struct parseq_engine {
   parseq_config cfg;
-  int D, T, Kp, Me, Md, L, V, C, gh, gw, dh_dec;
+  int D, T, Kp, Me, Md, L, V, C, gh, gw, dh_dec;   // T: tokens per image in the encoder (patches + class token if any)
+  int arch = 0, Tp = 0;                              // arch 1 = ViTSTR; Tp = gh * gw patches
+  std::map<std::string, int> pub_index;
+  float* vt_rows = nullptr;                          // ViTSTR tail: gathered token rows [chunk * L, D] fp32
   int chunk;
   std::vector<Slot> slots;
   std::map<std::string, int> index;
@@ -349,8 +355,11 @@ struct parseq_engine {
 namespace {
 
 void add_slot(parseq_engine* e, const std::string& key, long long numel, bool bf16) {
+  std::string pub = key;
+  if (e->arch == 1 && key.rfind("encoder.", 0) == 0) pub = key.substr(8);
   e->index[key] = static_cast<int>(e->slots.size());
-  e->slots.push_back(Slot{key, numel, bf16, nullptr, false});
+  e->pub_index[pub] = static_cast<int>(e->slots.size());
+  e->slots.push_back(Slot{key, pub, numel, bf16, nullptr, false});
 }
 
 template <typename Tp>
@@ -381,6 +390,7 @@ int alloc_workspace(parseq_engine* e) {
   PQ_TRY(dev_alloc(&e->ar_ids, 1ll * e->max_batch * 32));
   PQ_TRY(dev_alloc(&e->ar_bar, 64));
   PQ_TRY(dev_alloc(&e->ar_prof, 32 * 16));
+  if (e->arch == 1) PQ_TRY(dev_alloc(&e->vt_rows, 1ll * e->chunk * e->L * D));
   PQ_CUDA(cudaEventCreateWithFlags(&e->ev_enc, cudaEventDisableTiming));
   const int n_stages = (e->max_batch + e->dec_chunk - 1) / e->dec_chunk;
   e->stages.resize(static_cast<size_t>(n_stages));
@@ -416,6 +426,7 @@ void free_workspace(parseq_engine* e) {
   void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->mem, e->ckv, e->in_images, e->out_logits, e->out_ids,
                   e->out_steps, e->in_images_u8, e->ar_sa, e->ar_ca, e->ar_hd, e->ar_y, e->ar_qc, e->ar_part, e->ar_ids, e->ar_bar, e->ar_prof};
   e->ar_part = nullptr; e->ar_prof = nullptr; e->in_images_u8 = nullptr;
+  if (e->vt_rows) { cudaFree(e->vt_rows); e->vt_rows = nullptr; }
   e->ar_sa = e->ar_ca = e->ar_hd = nullptr; e->ar_y = e->ar_qc = nullptr; e->ar_ids = nullptr; e->ar_bar = nullptr;
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -468,7 +479,7 @@ int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float
 
 // ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
 int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_bfloat16* mem_out, float* memory32,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool final_norm = true) {
   const int D = e->D, T = e->T, M = B * T;
   e->cur_cat = CAT_ENC_GEMM;
   {
@@ -485,10 +496,25 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
                       e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
     }
   }
-  // x = patches * Wpe^T + bpe + pos_embed
-  PQ_TRY(gemm(e, e->a_pe, e->Kp, e->w("encoder.patch_embed.proj.weight"), e->Kp,
-              e->wf("encoder.patch_embed.proj.bias"), M, D, e->Kp, pq::EPI_F32, 1.0f, e->wf("encoder.pos_embed"), D, T,
-              e->x, D, st));
+  if (e->arch == 0) {
+    // x = patches * Wpe^T + bpe + pos_embed
+    PQ_TRY(gemm(e, e->a_pe, e->Kp, e->w("encoder.patch_embed.proj.weight"), e->Kp,
+                e->wf("encoder.patch_embed.proj.bias"), M, D, e->Kp, pq::EPI_F32, 1.0f, e->wf("encoder.pos_embed"), D, T,
+                e->x, D, st));
+  } else {
+    // timm _pos_embed with a class token: x = cat(cls_token, patches * Wpe^T + bpe) + pos_embed[0..Tp]
+    float* tmp = reinterpret_cast<float*>(e->hid);      // [B*Tp, D] fp32 fits the (still unused) [B*T, 4D] bf16 MLP buffer
+    PQ_TRY(gemm(e, e->a_pe, e->Kp, e->w("encoder.patch_embed.proj.weight"), e->Kp,
+                e->wf("encoder.patch_embed.proj.bias"), B * e->Tp, D, e->Kp, pq::EPI_F32, 1.0f,
+                e->wf("encoder.pos_embed") + D, D, e->Tp, tmp, D, st));
+    TimedScope ts(e, st, CAT_MISC, 0.0);
+    const long long total = 1ll * M * (D / 4);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148ll * 16));
+    PQ_TRY(launch_k(pq::cls_assemble_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(tmp),
+                    reinterpret_cast<const float4*>(e->wf("encoder.cls_token")),
+                    reinterpret_cast<const float4*>(e->wf("encoder.pos_embed")), reinterpret_cast<float4*>(e->x), B, e->Tp,
+                    D / 4));
+  }
   for (int i = 0; i < e->cfg.enc_depth; ++i) {
     const std::string p = "encoder.blocks." + std::to_string(i) + ".";
     PQ_TRY(layernorm(e, e->x, p + "norm1", 1e-6f, M, e->xn, nullptr, st));
@@ -506,7 +532,28 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
     PQ_TRY(gemm(e, e->hid, e->Me, e->w(p + "mlp.fc2.weight"), e->Me, e->wf(p + "mlp.fc2.bias"), M, D, e->Me,
                 pq::EPI_F32, 1.0f, e->x, D, 0, e->x, D, st));
   }
-  PQ_TRY(layernorm(e, e->x, "encoder.norm", 1e-6f, M, mem_out, memory32, st));
+  if (final_norm) PQ_TRY(layernorm(e, e->x, "encoder.norm", 1e-6f, M, mem_out, memory32, st));
+  return PARSEQ_OK;
+}
+
+// ---------------------------------------------------------------- ViTSTR tail (vitstr/model.py:19-28, vitstr/system.py:65-71)
+// logits[b, j] = head(norm(x[b, 1 + j])), j < L = max_length + 1: the reference computes tokens [0, max_length + 2) and
+// drops token 0 (the class token); norm and head are row-wise, so only the kept rows are gathered and computed.
+int argmax_rows(parseq_engine* e, const float* logits, int L, int B, int nrows, int src0, int* ids, int ids_ld, int dst0,
+                const int* forced, int forced_ld, cudaStream_t st);
+int vitstr_tail(parseq_engine* e, int B, int L, float* logits, int* ids_out, cudaStream_t st) {
+  const int D = e->D, M = B * L;
+  {
+    TimedScope ts(e, st, CAT_MISC, 0.0);
+    const long long total = 1ll * M * (D / 4);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148ll * 16));
+    PQ_TRY(launch_k(pq::gather_token_rows_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(e->x),
+                    reinterpret_cast<float4*>(e->vt_rows), B, e->T, 1, L, D / 4));
+  }
+  PQ_TRY(layernorm(e, e->vt_rows, "encoder.norm", 1e-6f, M, e->xn, nullptr, st));
+  PQ_TRY(gemm(e, e->xn, D, e->w("head.weight"), D, e->wf("head.bias"), M, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0, logits,
+              e->C, st));
+  if (ids_out != nullptr) PQ_TRY(argmax_rows(e, logits, L, B, L, 0, ids_out, L, 0, nullptr, 0, st));
   return PARSEQ_OK;
 }
 
@@ -681,6 +728,14 @@ int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B,
                   float* logits, int* ids_out, int* steps) {
   const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w * (u8 ? 1 : 4);   // bytes per image
   const int D = e->D, T = e->T;
+  if (e->arch == 1) {               // ViTSTR: encoder blocks, then norm + head on the kept token rows of each chunk
+    for (int o = 0; o < B; o += e->chunk) {
+      const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
+      PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, nullptr, nullptr, e->main, false));
+      PQ_TRY(vitstr_tail(e, Bs, L, logits + 1ll * o * L * e->C, ids_out ? ids_out + 1ll * o * L : nullptr, e->main));
+    }
+    return PARSEQ_OK;
+  }
   for (int o = 0; o < B; o += e->chunk) {
     const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
     PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
@@ -769,7 +824,8 @@ int forward_impl(parseq_engine* e, const parseq_forward_args* a, const void* ima
   // user stream -> main
   PQ_CUDA(cudaEventRecord(e->ev_in, user));
   PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
-  PQ_TRY(launch_k(pq::set_int_kernel, dim3(1), dim3(32), 0, e->main, e->out_steps, (testing && a->decode_ar) ? 0 : L));
+  PQ_TRY(launch_k(pq::set_int_kernel, dim3(1), dim3(32), 0, e->main, e->out_steps,
+                  (testing && a->decode_ar && e->arch == 0) ? 0 : L));
   e->launches++;
   for (int b0 = 0; b0 < a->batch; b0 += e->max_batch) {
     const int Bc = (a->batch - b0 < e->max_batch) ? (a->batch - b0) : e->max_batch;
@@ -819,19 +875,29 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   g_sm_count = prop.multiProcessorCount;
   PQ_TRY(init_kernel_attributes());
   PQ_TRY(load_driver_api());
-  if (cfg->dec_depth != 1) return fail(PARSEQ_ERR_UNSUPPORTED, "dec_depth must be 1");
+  if (cfg->arch != 0 && cfg->arch != 1) return fail(PARSEQ_ERR_INVALID_ARG, "arch: 0 (PARSeq) or 1 (ViTSTR)");
+  const bool vitstr = cfg->arch == 1;
+  if (!vitstr && cfg->dec_depth != 1) return fail(PARSEQ_ERR_UNSUPPORTED, "dec_depth must be 1");
   if (cfg->img_h % cfg->patch_h || cfg->img_w % cfg->patch_w) return fail(PARSEQ_ERR_INVALID_ARG, "img/patch mismatch");
   const int D = cfg->embed_dim;
   if (D != 192 && D != 384 && D != 768) return fail(PARSEQ_ERR_UNSUPPORTED, "embed_dim must be 192, 384 or 768");
   if (D != cfg->enc_num_heads * 64) return fail(PARSEQ_ERR_UNSUPPORTED, "encoder head_dim must be 64");
-  if (D != cfg->dec_num_heads * 32) return fail(PARSEQ_ERR_UNSUPPORTED, "decoder head_dim must be 32");
+  if (!vitstr && D != cfg->dec_num_heads * 32) return fail(PARSEQ_ERR_UNSUPPORTED, "decoder head_dim must be 32");
   if (cfg->max_label_length + 1 > 32) return fail(PARSEQ_ERR_UNSUPPORTED, "max_label_length must be <= 31");
   auto* e = new parseq_engine();
   e->cfg = *cfg;
+  if (vitstr) {                     // no decoder: neutral values keep the (unused) decoder workspace sizes sane
+    e->cfg.dec_num_heads = D / 32;
+    e->cfg.dec_mlp_ratio = 1;
+    e->cfg.dec_depth = 0;
+  }
+  cfg = &e->cfg;
+  e->arch = cfg->arch;
   e->D = D;
   e->gh = cfg->img_h / cfg->patch_h;
   e->gw = cfg->img_w / cfg->patch_w;
-  e->T = e->gh * e->gw;
+  e->Tp = e->gh * e->gw;
+  e->T = e->Tp + (vitstr ? 1 : 0);   // class token (timm VisionTransformer default, kept by vitstr/model.py)
   e->Kp = 3 * cfg->patch_h * cfg->patch_w;
   e->Me = D * cfg->enc_mlp_ratio;
   e->Md = D * cfg->dec_mlp_ratio;
@@ -848,8 +914,14 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
     delete e;
     return fail(PARSEQ_ERR_UNSUPPORTED, "at most 256 image tokens (img_size / patch_size) are supported");
   }
+  if (vitstr && e->Tp < e->L) {     // vitstr/model.py:21 slices max_length + 2 tokens out of the T + 1 available
+    delete e;
+    return fail(PARSEQ_ERR_UNSUPPORTED, "ViTSTR needs at least max_label_length + 1 patches");
+  }
   if ((e->Kp * 2) % 16 != 0) { delete e; return fail(PARSEQ_ERR_UNSUPPORTED, "patch dim must be a multiple of 8"); }
   // ---- weight slots: state_dict keys of strhub.models.parseq.model.PARSeq ----
+  // ---- (arch 1: keys of vitstr.model.ViTSTR = timm VisionTransformer; the public names drop "encoder.") ----
+  if (vitstr) add_slot(e, "encoder.cls_token", D, false);
   add_slot(e, "encoder.pos_embed", 1ll * e->T * D, false);
   add_slot(e, "encoder.patch_embed.proj.weight", 1ll * D * e->Kp, true);
   add_slot(e, "encoder.patch_embed.proj.bias", D, false);
@@ -871,26 +943,30 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   add_slot(e, "encoder.norm.weight", D, false);
   add_slot(e, "encoder.norm.bias", D, false);
   const std::string Ly = "decoder.layers.0.";
-  for (const char* att : {"self_attn", "cross_attn"}) {
-    add_slot(e, Ly + att + ".in_proj_weight", 3ll * D * D, true);
-    add_slot(e, Ly + att + ".in_proj_bias", 3 * D, false);
-    add_slot(e, Ly + att + ".out_proj.weight", 1ll * D * D, true);
-    add_slot(e, Ly + att + ".out_proj.bias", D, false);
+  if (!vitstr) {
+    for (const char* att : {"self_attn", "cross_attn"}) {
+      add_slot(e, Ly + att + ".in_proj_weight", 3ll * D * D, true);
+      add_slot(e, Ly + att + ".in_proj_bias", 3 * D, false);
+      add_slot(e, Ly + att + ".out_proj.weight", 1ll * D * D, true);
+      add_slot(e, Ly + att + ".out_proj.bias", D, false);
+    }
+    add_slot(e, Ly + "linear1.weight", 1ll * e->Md * D, true);
+    add_slot(e, Ly + "linear1.bias", e->Md, false);
+    add_slot(e, Ly + "linear2.weight", 1ll * D * e->Md, true);
+    add_slot(e, Ly + "linear2.bias", D, false);
+    for (const char* n : {"norm1", "norm2", "norm_q", "norm_c"}) {
+      add_slot(e, Ly + n + ".weight", D, false);
+      add_slot(e, Ly + n + ".bias", D, false);
+    }
+    add_slot(e, "decoder.norm.weight", D, false);
+    add_slot(e, "decoder.norm.bias", D, false);
   }
-  add_slot(e, Ly + "linear1.weight", 1ll * e->Md * D, true);
-  add_slot(e, Ly + "linear1.bias", e->Md, false);
-  add_slot(e, Ly + "linear2.weight", 1ll * D * e->Md, true);
-  add_slot(e, Ly + "linear2.bias", D, false);
-  for (const char* n : {"norm1", "norm2", "norm_q", "norm_c"}) {
-    add_slot(e, Ly + n + ".weight", D, false);
-    add_slot(e, Ly + n + ".bias", D, false);
-  }
-  add_slot(e, "decoder.norm.weight", D, false);
-  add_slot(e, "decoder.norm.bias", D, false);
   add_slot(e, "head.weight", 1ll * e->C * D, true);
   add_slot(e, "head.bias", e->C, false);
-  add_slot(e, "text_embed.embedding.weight", 1ll * e->V * D, false);
-  add_slot(e, "pos_queries", 1ll * e->L * D, false);
+  if (!vitstr) {
+    add_slot(e, "text_embed.embedding.weight", 1ll * e->V * D, false);
+    add_slot(e, "pos_queries", 1ll * e->L * D, false);
+  }
   for (auto& s : e->slots) {
     // +64 elements of slack: head.bias (95 floats) is read with float4 only when in range, but keep
     // every buffer 16-byte padded
@@ -931,13 +1007,13 @@ int parseq_num_weights(const parseq_engine* e) { return e ? static_cast<int>(e->
 const char* parseq_weight_key(const parseq_engine* e, int i, int64_t* numel) {
   if (e == nullptr || i < 0 || i >= static_cast<int>(e->slots.size())) return nullptr;
   if (numel) *numel = e->slots[i].numel;
-  return e->slots[i].key.c_str();
+  return e->slots[i].pub.c_str();
 }
 
 int parseq_set_weight(parseq_engine* e, const char* key, const float* data, int64_t numel) {
   if (e == nullptr || key == nullptr || data == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
-  auto it = e->index.find(key);
-  if (it == e->index.end()) return fail(PARSEQ_ERR_INVALID_ARG, std::string("unexpected state_dict key: ") + key);
+  auto it = e->pub_index.find(key);
+  if (it == e->pub_index.end()) return fail(PARSEQ_ERR_INVALID_ARG, std::string("unexpected state_dict key: ") + key);
   Slot& s = e->slots[it->second];
   if (numel != s.numel)
     return fail(PARSEQ_ERR_INVALID_ARG, std::string("size mismatch for ") + key + ": got " + std::to_string(numel) +
@@ -958,8 +1034,12 @@ int parseq_set_weight(parseq_engine* e, const char* key, const float* data, int6
 int parseq_finalize(parseq_engine* e, parseq_stream_t stream) {
   if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
   for (auto& s : e->slots)
-    if (!s.set) return fail(PARSEQ_ERR_STATE, "weight not set: " + s.key);
+    if (!s.set) return fail(PARSEQ_ERR_STATE, "weight not set: " + s.pub);
   PQ_CUDA(cudaSetDevice(e->cfg.device));
+  if (e->arch == 1) {               // ViTSTR has no input-independent tables
+    e->finalized = true;
+    return PARSEQ_OK;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int D = e->D, L = e->L, V = e->V;
   const std::string Ly = "decoder.layers.0.";
@@ -1092,6 +1172,7 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (n == "attn_impl") { g_attn_impl = value != 0 ? 1 : 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "pdl") { g_use_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
+  if (n == "gemm_stages") { g_gemm_stages = value > 0 ? static_cast<int>(value) : 0; return PARSEQ_OK; }
   if (n == "cta_group") {
     if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "cta_group: 0 (auto) / 1 / 2");
     g_cta_group_override = static_cast<int>(value);

@@ -33,6 +33,7 @@ struct GemmParams {
   int tma_out;         // 0: direct stores (fallback), 1: TMA store fp32, 2: TMA reduce-add fp32 (out += ...),
                        // 3: TMA store bf16 (mode EPI_BF16 / EPI_GELU_BF16)
   int num_m_tiles, num_n_tiles;  // in units of (128 * CG) x BLOCK_N
+  int max_stages;                // 0: the full operand ring; n > 0: use only n slots (pipeline-depth experiments)
 };
 
 constexpr int GEMM_BLOCK_M = 128;  // rows per CTA (one TMEM lane per row)
@@ -50,8 +51,13 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
   static constexpr int kBBytes = kBRows * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 2 * 4096;  // per epilogue warp: 2 buffers x (32 rows x 128 B)
-  static constexpr int kBiasBytes = GEMM_EPI_WARPS * BLOCK_N * 4;   // per-warp copy of the tile's bias slice
+  // Shared memory is what bounds the TMA pipeline depth, so the widest tile trades epilogue buffering for a 4th
+  // operand stage: BLOCK_N = 256 keeps ONE staging slab per epilogue warp (the previous store's smem read is
+  // hidden behind the next chunk's TMEM load + math) and ONE bias slice shared by all epilogue warps.
+  static constexpr int kSlabs = (BLOCK_N == 256) ? 1 : 2;           // staging slabs (32 rows x 128 B) per epilogue warp
+  static constexpr bool kSharedBias = (BLOCK_N == 256);
+  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * kSlabs * 4096;
+  static constexpr int kBiasBytes = (kSharedBias ? 1 : GEMM_EPI_WARPS) * BLOCK_N * 4;  // bias slice of the current tile
   static constexpr int kStagesRaw = (232448 - 1024 - 256 - kEpiStageBytes - kBiasBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -63,15 +69,20 @@ struct GemmCfg {
   static_assert(kStages >= 3, "pipeline depth");
 };
 
+// named barrier over the 8 epilogue warps only (barrier 0 stays __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ epilogue bodies
 // One epilogue warp owns 32 accumulator rows (its TMEM lane quarter); the two warps of a quarter alternate chunks.
 // TMA path: TMEM -> registers -> (+bias, activation) -> 128B-swizzled smem slab (32 rows x 128 B) -> TMA store /
 // fp32 reduce-add; out-of-range rows / columns are clipped by the tensor map, nothing is ever loaded from global.
-template <int BLOCK_N, bool REDUCE>
+template <int BLOCK_N, bool REDUCE, int SLABS>
 __device__ __forceinline__ void epi_tma_f32(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, uint8_t* my_stage,
                                             const float* my_bias, int n0, int row0, int half, int lane, int& it) {
-  // `it` counts this warp's TMA stores over the whole kernel: slab (it & 1) is free once at most one newer store
-  // is still reading its source (bulk_wait_group_read<1>), so the counter must NOT restart per tile.
+  // `it` counts this warp's TMA stores over the whole kernel: slab (it % SLABS) is free once at most SLABS-1 newer
+  // stores are still reading their source (bulk_wait_group_read<SLABS-1>), so the counter must NOT restart per tile.
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
 #pragma unroll 1
   for (int c = half; c < BLOCK_N / 32; c += 2, ++it) {
@@ -80,20 +91,17 @@ __device__ __forceinline__ void epi_tma_f32(const GemmParams& p, const CUtensorM
     uint32_t v[32];
     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
     tmem_ld_wait();
-    if (lane == 0) bulk_wait_group_read<1>();
-    __syncwarp();
-    uint8_t* slab = my_stage + (it & 1) * 4096;
-    uint8_t* buf = slab + lane * 128;
     const float* bb = my_bias + c * 32;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      float4 q;
-      q.x = (__uint_as_float(v[jj * 4 + 0]) + bb[jj * 4 + 0]) * p.alpha;
-      q.y = (__uint_as_float(v[jj * 4 + 1]) + bb[jj * 4 + 1]) * p.alpha;
-      q.z = (__uint_as_float(v[jj * 4 + 2]) + bb[jj * 4 + 2]) * p.alpha;
-      q.w = (__uint_as_float(v[jj * 4 + 3]) + bb[jj * 4 + 3]) * p.alpha;
-      *reinterpret_cast<float4*>(buf + ((static_cast<uint32_t>(jj) ^ sw) << 4)) = q;
-    }
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + bb[j]) * p.alpha);
+    if (lane == 0) bulk_wait_group_read<SLABS - 1>();
+    __syncwarp();
+    uint8_t* slab = my_stage + (it % SLABS) * 4096;
+    uint8_t* buf = slab + lane * 128;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(jj) ^ sw) << 4)) =
+          make_uint4(v[jj * 4 + 0], v[jj * 4 + 1], v[jj * 4 + 2], v[jj * 4 + 3]);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -104,7 +112,7 @@ __device__ __forceinline__ void epi_tma_f32(const GemmParams& p, const CUtensorM
   }
 }
 
-template <int BLOCK_N, bool GELU>
+template <int BLOCK_N, bool GELU, int SLABS>
 __device__ __forceinline__ void epi_tma_bf16(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr, uint8_t* my_stage,
                                              const float* my_bias, int n0, int row0, int half, int lane, int& it) {
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -112,17 +120,12 @@ __device__ __forceinline__ void epi_tma_bf16(const GemmParams& p, const CUtensor
   for (int c = half; c < BLOCK_N / 64; c += 2, ++it) {   // 64 bf16 columns = 128 B per row per TMA store
     const int col0 = n0 + c * 64;
     if (col0 >= p.N) break;
-    uint8_t* slab = my_stage + (it & 1) * 4096;
-    uint8_t* buf = slab + lane * 128;
+    uint4 q[8];                          // this lane's 64 output columns, packed (held across the slab wait)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 64 + h * 32), v);
       tmem_ld_wait();
-      if (h == 0) {
-        if (lane == 0) bulk_wait_group_read<1>();
-        __syncwarp();
-      }
       const float* bb = my_bias + c * 64 + h * 32;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -132,12 +135,17 @@ __device__ __forceinline__ void epi_tma_bf16(const GemmParams& p, const CUtensor
           const float a = __uint_as_float(v[jj * 8 + t]) + bb[jj * 8 + t];
           f[t] = GELU ? gelu_erf(a) : a * p.alpha;
         }
-        uint4 q;
-        q.x = pack_bf16(f[0], f[1]); q.y = pack_bf16(f[2], f[3]);
-        q.z = pack_bf16(f[4], f[5]); q.w = pack_bf16(f[6], f[7]);
-        *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(h * 4 + jj) ^ sw) << 4)) = q;
+        q[h * 4 + jj].x = pack_bf16(f[0], f[1]); q[h * 4 + jj].y = pack_bf16(f[2], f[3]);
+        q[h * 4 + jj].z = pack_bf16(f[4], f[5]); q[h * 4 + jj].w = pack_bf16(f[6], f[7]);
       }
     }
+    if (lane == 0) bulk_wait_group_read<SLABS - 1>();   // the store that last read this slab is done with it
+    __syncwarp();
+    uint8_t* slab = my_stage + (it % SLABS) * 4096;
+    uint8_t* buf = slab + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(j) ^ sw) << 4)) = q[j];
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -250,6 +258,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_clusters = gridDim.x / CG;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;    // tiles of (128*CG) x BLOCK_N
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int nstages = (p.max_stages > 0 && p.max_stages < Cfg::kStages) ? p.max_stages : Cfg::kStages;
 
   grid_dep_launch();                       // PDL: the next kernel may start its own prologue
   if (warp == 0 && lane == 0) {
@@ -299,7 +308,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tma_load_2d_pair(sa, &tmA, leader_full, kb * GEMM_BLOCK_K, m0);
             tma_load_2d_pair(sb, &tmB, leader_full, kb * GEMM_BLOCK_K, n0);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -332,7 +341,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           // smem slot reusable (in every CTA of the group) once these MMAs have read it
           if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         // accumulator complete (signalled to the epilogue warps of every CTA of the group)
         if constexpr (CG == 2) umma_commit_pair(&tfull_bar[as], 0x3); else umma_commit(&tfull_bar[as]);
@@ -345,30 +354,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int ew = warp - 2;               // 0..7
     const int half = ew >> 2;              // which of the alternating column chunks this warp takes
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* my_stage = epi_base + ew * 8192;
-    float* my_bias = bias_base + ew * BLOCK_N;
+    uint8_t* my_stage = epi_base + ew * (Cfg::kSlabs * 4096);
+    float* my_bias = Cfg::kSharedBias ? bias_base : bias_base + ew * BLOCK_N;
     int as = 0;
     uint32_t aphase = 0;
     int store_it = 0;                      // running count of this warp's TMA stores (staging slab parity)
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = (tile / p.num_n_tiles) * (GEMM_BLOCK_M * CG) + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      if (p.tma_out != 0) {                // bias slice of this tile -> this warp's smem copy (before the wait)
-        __syncwarp();
-        for (int j = lane; j < BLOCK_N; j += 32)
-          my_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.0f;
-        __syncwarp();
+      if (p.tma_out != 0) {                // bias slice of this tile -> smem (before the accumulator wait)
+        if constexpr (Cfg::kSharedBias) {  // one copy for the 8 epilogue warps, one element per thread
+          static_assert(!Cfg::kSharedBias || BLOCK_N == 32 * GEMM_EPI_WARPS, "one bias element per epilogue thread");
+          epi_bar_sync();                  // every warp is done reading the previous tile's slice
+          const int j = ew * 32 + lane;
+          bias_base[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.0f;
+          epi_bar_sync();
+        } else {
+          __syncwarp();
+          for (int j = lane; j < BLOCK_N; j += 32)
+            my_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.0f;
+          __syncwarp();
+        }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * BLOCK_N);
       const int row0 = m0 + quarter * 32;
-      if (p.tma_out == 2) epi_tma_f32<BLOCK_N, true>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
-      else if (p.tma_out == 1) epi_tma_f32<BLOCK_N, false>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+      if (p.tma_out == 2) epi_tma_f32<BLOCK_N, true, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+      else if (p.tma_out == 1) epi_tma_f32<BLOCK_N, false, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
       else if (p.tma_out == 3) {
-        if (p.mode == EPI_GELU_BF16) epi_tma_bf16<BLOCK_N, true>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
-        else epi_tma_bf16<BLOCK_N, false>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+        if (p.mode == EPI_GELU_BF16) epi_tma_bf16<BLOCK_N, true, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
+        else epi_tma_bf16<BLOCK_N, false, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
       } else {
         epi_direct<BLOCK_N>(p, taddr, n0, m0 + row_in_tile, half);
       }

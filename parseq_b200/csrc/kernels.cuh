@@ -764,6 +764,47 @@ __global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// ViTSTR (vitstr/model.py:14-28 over timm VisionTransformer._pos_embed): token 0 of every image is
+// cls_token + pos_embed[0]; tokens 1..Tp are the patch embeddings (pos_embed[1..Tp] already added by the patch GEMM).
+__global__ void cls_assemble_kernel(const float4* __restrict__ patches, const float4* __restrict__ cls,
+                                    const float4* __restrict__ pos0, float4* __restrict__ x, int B, int Tp, int D4) {
+  grid_dep_launch();
+  grid_dep_wait();                 // launched with the PDL attribute: the patch GEMM's output is complete from here on
+  const long long total = static_cast<long long>(B) * (Tp + 1) * D4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D4);
+    const long long row = i / D4;
+    const int t = static_cast<int>(row % (Tp + 1));
+    const long long b = row / (Tp + 1);
+    float4 v;
+    if (t == 0) {
+      const float4 a = cls[c], p = pos0[c];
+      v = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    } else {
+      v = patches[(b * Tp + (t - 1)) * D4 + c];
+    }
+    x[i] = v;
+  }
+}
+// out[b, j, :] = x[b, first + j, :], j < n (the `x[:, :seqlen]` / `logits[:, 1:]` slices of vitstr/model.py:21,
+// vitstr/system.py:70 applied BEFORE norm + head: both are row-wise, so only the kept rows are computed).
+__global__ void gather_token_rows_kernel(const float4* __restrict__ x, float4* __restrict__ out, int B, int T, int first,
+                                         int n, int D4) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long total = static_cast<long long>(B) * n * D4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D4);
+    const long long row = i / D4;
+    const int j = static_cast<int>(row % n);
+    const long long b = row / n;
+    out[i] = x[(b * T + first + j) * D4 + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused tail of a decoder pass: out = LayerNorm(y; decoder.norm) -> logits = head(out) -> greedy argmax
 // (modules.py:124 `Decoder.norm`, model.py:138 `self.head`, model.py:142 argmax).  4 rows per CTA; the head weight
 // (C x D bf16, 73 KB for 95 x 384) is staged in shared memory with an odd word pitch (lane = class reads are

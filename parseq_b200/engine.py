@@ -15,7 +15,7 @@ _lib = None
 class ParseqConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "img_h", "img_w", "patch_h", "patch_w", "embed_dim", "enc_num_heads", "enc_mlp_ratio", "enc_depth",
-        "dec_num_heads", "dec_mlp_ratio", "dec_depth", "max_label_length", "num_tokens", "max_batch", "device")]
+        "dec_num_heads", "dec_mlp_ratio", "dec_depth", "max_label_length", "num_tokens", "max_batch", "device", "arch")]
 
 
 class ForwardArgsC(C.Structure):
@@ -92,7 +92,8 @@ class Engine:
         self.cfg = cfg
         c = ParseqConfigC(cfg.img_size[0], cfg.img_size[1], cfg.patch_size[0], cfg.patch_size[1], cfg.embed_dim,
                           cfg.enc_num_heads, cfg.enc_mlp_ratio, cfg.enc_depth, cfg.dec_num_heads, cfg.dec_mlp_ratio,
-                          cfg.dec_depth, cfg.max_label_length, cfg.num_tokens, max_batch, device)
+                          cfg.dec_depth, cfg.max_label_length, cfg.num_tokens, max_batch, device,
+                          1 if getattr(cfg, "arch", "parseq") == "vitstr" else 0)
         h = C.c_void_p()
         check(self.lib, self.lib.parseq_create(C.byref(c), C.byref(h)))
         self.handle = h

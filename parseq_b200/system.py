@@ -68,14 +68,14 @@ def _register(root: nn.Module, key: str, tensor: Tensor):
     mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
 
 
-class ParseqModel(nn.Module):
+class _EngineModule(nn.Module):
+    """Owns the parameters (reference state_dict names) and the lazily created engine handle."""
+
     def __init__(self, cfg: ParseqConfig):
         super().__init__()
         from .weights import init_state_dict
         self.cfg = cfg
         self.max_label_length = cfg.max_label_length
-        self.decode_ar = cfg.decode_ar
-        self.refine_iters = cfg.refine_iters
         # random init with the reference's distributions (weights.py); bf16-exact not forced here
         for k, v in init_state_dict(cfg, seed=0, perturb=False, bf16_exact=False).items():
             _register(self, k, v)
@@ -86,7 +86,7 @@ class ParseqModel(nn.Module):
     # ---- engine plumbing -------------------------------------------------------------------
     @property
     def _device(self) -> torch.device:
-        return self.pos_queries.device
+        return next(self.parameters()).device
 
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -126,14 +126,48 @@ class ParseqModel(nn.Module):
             raise AssertionError(f"Input image size {tuple(images.shape)} doesn't match model (N,3,{H},{W})")
         return images.to(torch.float32).contiguous()
 
-    # ---- reference API ---------------------------------------------------------------------
-    def encode(self, img: Tensor) -> Tensor:
+    def _features(self, img: Tensor) -> Tensor:
+        """timm forward_features of the ViT: fp32 [N, tokens, D]."""
         eng = self.engine()
         img = self._check_images(img)
-        mem = torch.empty((img.shape[0], self.cfg.num_patches, self.cfg.embed_dim), dtype=torch.float32,
+        if img.dtype == torch.uint8:
+            raise AssertionError("encode / forward_features take normalised float images")
+        mem = torch.empty((img.shape[0], self.cfg.enc_tokens, self.cfg.embed_dim), dtype=torch.float32,
                           device=img.device)
         eng.encode(img.data_ptr(), img.shape[0], mem.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream)
         return mem
+
+    def _run(self, images: Tensor, max_length, decode_ar, refine_iters, forced_ids=None, forced_refine=None):
+        eng = self.engine()
+        images = self._check_images(images)
+        dev = images.device
+        N = images.shape[0]
+        L = eng.num_steps(max_length)
+        logits = torch.empty((N, L, self.cfg.num_classes), dtype=torch.float32, device=dev)
+        ids = torch.empty((N, L), dtype=torch.int32, device=dev)
+        steps = torch.empty((1,), dtype=torch.int32, device=dev)
+        fi = forced_ids.to(device=dev, dtype=torch.int32).contiguous() if forced_ids is not None else None
+        fr = forced_refine.to(device=dev, dtype=torch.int32).contiguous() if forced_refine is not None else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if images.dtype == torch.uint8:
+            eng.forward_u8(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(), st, max_length,
+                           decode_ar, refine_iters)
+        else:
+            eng.forward(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(), st, max_length,
+                        decode_ar, refine_iters, fi.data_ptr() if fi is not None else None,
+                        fr.data_ptr() if fr is not None else None)
+        return logits, ids, steps
+
+
+class ParseqModel(_EngineModule):
+    def __init__(self, cfg: ParseqConfig):
+        super().__init__(cfg)
+        self.decode_ar = cfg.decode_ar
+        self.refine_iters = cfg.refine_iters
+
+    # ---- reference API ---------------------------------------------------------------------
+    def encode(self, img: Tensor) -> Tensor:
+        return self._features(img)
 
     def decode(self, *args, **kwargs):
         raise NotImplementedError("arbitrary-mask decode() is a training-time API (system.py:169-200) and is not "
@@ -142,24 +176,7 @@ class ParseqModel(nn.Module):
     def forward(self, tokenizer: Tokenizer, images: Tensor, max_length: Optional[int] = None,
                 return_ids: bool = False, forced_ids: Optional[Tensor] = None,
                 forced_refine: Optional[Tensor] = None):
-        eng = self.engine()
-        images = self._check_images(images)
-        dev = images.device
-        N = images.shape[0]
-        L = eng.num_steps(max_length)
-        C = self.cfg.num_classes
-        logits = torch.empty((N, L, C), dtype=torch.float32, device=dev)
-        ids = torch.empty((N, L), dtype=torch.int32, device=dev)
-        steps = torch.empty((1,), dtype=torch.int32, device=dev)
-        fi = forced_ids.to(device=dev, dtype=torch.int32).contiguous() if forced_ids is not None else None
-        fr = forced_refine.to(device=dev, dtype=torch.int32).contiguous() if forced_refine is not None else None
-        if images.dtype == torch.uint8:
-            eng.forward_u8(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(),
-                           torch.cuda.current_stream(dev).cuda_stream, max_length, self.decode_ar, self.refine_iters)
-        else:
-            eng.forward(images.data_ptr(), N, logits.data_ptr(), ids.data_ptr(), steps.data_ptr(),
-                        torch.cuda.current_stream(dev).cuda_stream, max_length, self.decode_ar, self.refine_iters,
-                        fi.data_ptr() if fi is not None else None, fr.data_ptr() if fr is not None else None)
+        logits, ids, steps = self._run(images, max_length, self.decode_ar, self.refine_iters, forced_ids, forced_refine)
         if max_length is None and self.decode_ar and not self.refine_iters:
             # model.py:144-147: with no refinement the reference returns only the S steps it ran
             S = int(steps.item())
@@ -167,6 +184,24 @@ class ParseqModel(nn.Module):
         if return_ids:
             return logits, ids
         return logits
+
+
+class VitstrModel(_EngineModule):
+    """Mirror of `strhub.models.vitstr.model.ViTSTR` (vitstr/model.py:14-28): a timm ViT with class token whose head is
+    applied per token.  Parameters carry timm's names (`cls_token`, `pos_embed`, `blocks.<i>...`, `norm`, `head`)."""
+
+    def forward_features(self, x: Tensor) -> Tensor:
+        return self._features(x)
+
+    def forward_tokens(self, images: Tensor, max_length: Optional[int] = None, return_ids: bool = False):
+        """`self.forward(images, max_length + 2)[:, 1:]` (vitstr/system.py:65-71) in one engine call."""
+        logits, ids, _ = self._run(images, max_length, False, 0)
+        return (logits, ids) if return_ids else logits
+
+    def forward(self, x: Tensor, seqlen: int = 25) -> Tensor:
+        raise NotImplementedError(
+            "the engine computes head(norm(x))[:, 1:seqlen] only: token 0 (the class token) is discarded by the only "
+            "reference caller (vitstr/system.py:68-70); use forward_tokens(images, max_length) or forward_features(x)")
 
 
 class _HParams(SimpleNamespace):
@@ -180,45 +215,18 @@ class _HParams(SimpleNamespace):
         return self.__dict__.keys()
 
 
-class PARSeq(nn.Module):
-    def __init__(self, charset_train: str, charset_test: str, max_label_length: int, batch_size: int = 384,
-                 lr: float = 7e-4, warmup_pct: float = 0.075, weight_decay: float = 0.0,
-                 img_size: Sequence[int] = (32, 128), patch_size: Sequence[int] = (4, 8), embed_dim: int = 384,
-                 enc_num_heads: int = 6, enc_mlp_ratio: int = 4, enc_depth: int = 12, dec_num_heads: int = 12,
-                 dec_mlp_ratio: int = 4, dec_depth: int = 1, perm_num: int = 6, perm_forward: bool = True,
-                 perm_mirrored: bool = True, decode_ar: bool = True, refine_iters: int = 1, dropout: float = 0.1,
-                 **kwargs: Any) -> None:
-        super().__init__()
-        hp = dict(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
-                  batch_size=batch_size, lr=lr, warmup_pct=warmup_pct, weight_decay=weight_decay,
-                  img_size=list(img_size), patch_size=list(patch_size), embed_dim=embed_dim,
-                  enc_num_heads=enc_num_heads, enc_mlp_ratio=enc_mlp_ratio, enc_depth=enc_depth,
-                  dec_num_heads=dec_num_heads, dec_mlp_ratio=dec_mlp_ratio, dec_depth=dec_depth, perm_num=perm_num,
-                  perm_forward=perm_forward, perm_mirrored=perm_mirrored, decode_ar=decode_ar,
-                  refine_iters=refine_iters, dropout=dropout)
-        hp.update(kwargs)
-        self.hparams = _HParams(**hp)
+class _System(nn.Module):
+    """The inference-side surface of `strhub.models.base.CrossEntropySystem` (base.py:36-44,112-143,179-207)."""
+
+    def _init_base(self, charset_train, charset_test, batch_size, lr, warmup_pct, weight_decay):
         self.tokenizer = Tokenizer(charset_train)
         self.charset_adapter = CharsetAdapter(charset_test)
         self.bos_id, self.eos_id, self.pad_id = self.tokenizer.bos_id, self.tokenizer.eos_id, self.tokenizer.pad_id
         self.batch_size, self.lr, self.warmup_pct, self.weight_decay = batch_size, lr, warmup_pct, weight_decay
-        cfg = ParseqConfig(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
-                           img_size=tuple(img_size), patch_size=tuple(patch_size), embed_dim=embed_dim,
-                           enc_num_heads=enc_num_heads, enc_mlp_ratio=enc_mlp_ratio, enc_depth=enc_depth,
-                           dec_num_heads=dec_num_heads, dec_mlp_ratio=dec_mlp_ratio, dec_depth=dec_depth,
-                           decode_ar=decode_ar, refine_iters=refine_iters, dropout=dropout,
-                           name=str(kwargs.get("name", "parseq")))
-        try:
-            self.model = ParseqModel(cfg)
-        except EngineError as e:  # pragma: no cover
-            raise InvalidModelError(str(e)) from e
 
     @property
     def device(self) -> torch.device:
         return self.model._device
-
-    def forward(self, images: Tensor, max_length: Optional[int] = None) -> Tensor:
-        return self.model.forward(self.tokenizer, images, max_length)
 
     def postprocess(self, logits: Tensor):
         """Device-side greedy decode of logits [N, L, C]: (labels, confidences) with the semantics of
@@ -265,3 +273,77 @@ class PARSeq(nn.Module):
         sd = {k[len("model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("model.")}
         model.model.load_state_dict(sd)
         return model
+
+
+class PARSeq(_System):
+    def __init__(self, charset_train: str, charset_test: str, max_label_length: int, batch_size: int = 384,
+                 lr: float = 7e-4, warmup_pct: float = 0.075, weight_decay: float = 0.0,
+                 img_size: Sequence[int] = (32, 128), patch_size: Sequence[int] = (4, 8), embed_dim: int = 384,
+                 enc_num_heads: int = 6, enc_mlp_ratio: int = 4, enc_depth: int = 12, dec_num_heads: int = 12,
+                 dec_mlp_ratio: int = 4, dec_depth: int = 1, perm_num: int = 6, perm_forward: bool = True,
+                 perm_mirrored: bool = True, decode_ar: bool = True, refine_iters: int = 1, dropout: float = 0.1,
+                 **kwargs: Any) -> None:
+        super().__init__()
+        hp = dict(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
+                  batch_size=batch_size, lr=lr, warmup_pct=warmup_pct, weight_decay=weight_decay,
+                  img_size=list(img_size), patch_size=list(patch_size), embed_dim=embed_dim,
+                  enc_num_heads=enc_num_heads, enc_mlp_ratio=enc_mlp_ratio, enc_depth=enc_depth,
+                  dec_num_heads=dec_num_heads, dec_mlp_ratio=dec_mlp_ratio, dec_depth=dec_depth, perm_num=perm_num,
+                  perm_forward=perm_forward, perm_mirrored=perm_mirrored, decode_ar=decode_ar,
+                  refine_iters=refine_iters, dropout=dropout)
+        hp.update(kwargs)
+        self.hparams = _HParams(**hp)
+        self._init_base(charset_train, charset_test, batch_size, lr, warmup_pct, weight_decay)
+        cfg = ParseqConfig(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
+                           img_size=tuple(img_size), patch_size=tuple(patch_size), embed_dim=embed_dim,
+                           enc_num_heads=enc_num_heads, enc_mlp_ratio=enc_mlp_ratio, enc_depth=enc_depth,
+                           dec_num_heads=dec_num_heads, dec_mlp_ratio=dec_mlp_ratio, dec_depth=dec_depth,
+                           decode_ar=decode_ar, refine_iters=refine_iters, dropout=dropout,
+                           name=str(kwargs.get("name", "parseq")))
+        try:
+            self.model = ParseqModel(cfg)
+        except EngineError as e:  # pragma: no cover
+            raise InvalidModelError(str(e)) from e
+
+    def forward(self, images: Tensor, max_length: Optional[int] = None) -> Tensor:
+        return self.model.forward(self.tokenizer, images, max_length)
+
+
+class ViTSTR(_System):
+    """Mirror of `strhub.models.vitstr.system.ViTSTR` (vitstr/system.py:29-71), inference side."""
+
+    def __init__(self, charset_train: str, charset_test: str, max_label_length: int, batch_size: int = 384,
+                 lr: float = 8.9e-4, warmup_pct: float = 0.075, weight_decay: float = 0.0,
+                 img_size: Sequence[int] = (224, 224), patch_size: Sequence[int] = (16, 16), embed_dim: int = 384,
+                 num_heads: int = 6, **kwargs: Any) -> None:
+        super().__init__()
+        hp = dict(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
+                  batch_size=batch_size, lr=lr, warmup_pct=warmup_pct, weight_decay=weight_decay,
+                  img_size=list(img_size), patch_size=list(patch_size), embed_dim=embed_dim, num_heads=num_heads)
+        hp.update(kwargs)
+        self.hparams = _HParams(**hp)
+        self._init_base(charset_train, charset_test, batch_size, lr, warmup_pct, weight_decay)
+        self.max_label_length = max_label_length
+        # depth=12, mlp_ratio=4, qkv_bias=True are fixed by the reference ctor (vitstr/system.py:50-59)
+        cfg = ParseqConfig(charset_train=charset_train, charset_test=charset_test, max_label_length=max_label_length,
+                           img_size=tuple(img_size), patch_size=tuple(patch_size), embed_dim=embed_dim,
+                           enc_num_heads=num_heads, enc_mlp_ratio=4, enc_depth=12, arch="vitstr",
+                           name=str(kwargs.get("name", "vitstr")))
+        try:
+            self.model = VitstrModel(cfg)
+        except EngineError as e:  # pragma: no cover
+            raise InvalidModelError(str(e)) from e
+
+    def forward(self, images: Tensor, max_length: Optional[int] = None) -> Tensor:
+        return self.model.forward_tokens(images, max_length)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path: str, map_location="cpu", **kwargs):
+        return super().load_from_checkpoint(checkpoint_path, map_location, **kwargs)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Released ViTSTR weights are saved from the SYSTEM (strhub/models/utils.py:80-82: `m = model`), i.e. with a
+        'model.' prefix; accept both layouts."""
+        if all(k.startswith("model.") for k in state_dict):
+            state_dict = {k[len("model."):]: v for k, v in state_dict.items()}
+        return self.model.load_state_dict(state_dict, strict=strict, **kw)

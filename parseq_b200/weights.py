@@ -33,6 +33,12 @@ def _tn(gen: torch.Generator, shape, std: float = 0.02) -> torch.Tensor:
 
 def gemm_weight_keys(cfg: ParseqConfig):
     """state_dict keys the engine stores in bf16 (tensor-core operands)."""
+    if getattr(cfg, "arch", "parseq") == "vitstr":
+        keys = ["patch_embed.proj.weight"]
+        for i in range(cfg.enc_depth):
+            p = f"blocks.{i}."
+            keys += [p + "attn.qkv.weight", p + "attn.proj.weight", p + "mlp.fc1.weight", p + "mlp.fc2.weight"]
+        return keys + ["head.weight"]
     keys = ["encoder.patch_embed.proj.weight"]
     for i in range(cfg.enc_depth):
         p = f"encoder.blocks.{i}."
@@ -68,6 +74,8 @@ def init_state_dict(cfg: ParseqConfig, seed: int = 0, perturb: bool = True,
             sd[prefix + ".weight"] = torch.ones(D)
             sd[prefix + ".bias"] = torch.zeros(D)
 
+    if getattr(cfg, "arch", "parseq") == "vitstr":
+        return _init_vitstr(cfg, g, sd, bias, ln, perturb, bf16_exact)
     # ---- encoder (timm ViT names) ----
     sd["encoder.pos_embed"] = _tn(g, (1, T, D))
     fan_in = 3 * ph * pw
@@ -107,6 +115,38 @@ def init_state_dict(cfg: ParseqConfig, seed: int = 0, perturb: bool = True,
     sd["text_embed.embedding.weight"] = _tn(g, (cfg.num_tokens, D))
     sd["pos_queries"] = _tn(g, (1, cfg.max_steps, D))
 
+    if bf16_exact:
+        for k in gemm_weight_keys(cfg):
+            sd[k] = sd[k].to(torch.bfloat16).to(torch.float32)
+    return sd
+
+
+def _init_vitstr(cfg, g, sd, bias, ln, perturb, bf16_exact):
+    """state_dict of strhub.models.vitstr.model.ViTSTR == timm VisionTransformer(class_token=True, num_classes=C)
+    (vitstr/system.py:50-61): no "encoder." prefix, `cls_token`, `pos_embed` over T+1 tokens, `head`."""
+    D, T = cfg.embed_dim, cfg.num_patches
+    ph, pw = cfg.patch_size
+    Me = D * cfg.enc_mlp_ratio
+    sd["cls_token"] = _tn(g, (1, 1, D)) if perturb else torch.zeros(1, 1, D)   # timm: normal(std=1e-6)
+    sd["pos_embed"] = _tn(g, (1, T + 1, D))
+    bound = (1.0 / (3 * ph * pw)) ** 0.5
+    sd["patch_embed.proj.weight"] = (torch.rand((D, 3, ph, pw), generator=g) * 2 - 1) * bound
+    sd["patch_embed.proj.bias"] = (torch.rand((D,), generator=g) * 2 - 1) * bound
+    for i in range(cfg.enc_depth):
+        p = f"blocks.{i}."
+        ln(p + "norm1")
+        sd[p + "attn.qkv.weight"] = _tn(g, (3 * D, D))
+        sd[p + "attn.qkv.bias"] = bias(3 * D)
+        sd[p + "attn.proj.weight"] = _tn(g, (D, D))
+        sd[p + "attn.proj.bias"] = bias(D)
+        ln(p + "norm2")
+        sd[p + "mlp.fc1.weight"] = _tn(g, (Me, D))
+        sd[p + "mlp.fc1.bias"] = bias(Me)
+        sd[p + "mlp.fc2.weight"] = _tn(g, (D, Me))
+        sd[p + "mlp.fc2.bias"] = bias(D)
+    ln("norm")
+    sd["head.weight"] = _tn(g, (cfg.num_classes, D))      # vitstr/system.py:61 -> init_weights: trunc-normal(0.02)
+    sd["head.bias"] = bias(cfg.num_classes)
     if bf16_exact:
         for k in gemm_weight_keys(cfg):
             sd[k] = sd[k].to(torch.bfloat16).to(torch.float32)

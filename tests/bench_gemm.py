@@ -8,7 +8,8 @@ from parseq_b200.engine import load_library, check
 lib = load_library()
 st = torch.cuda.current_stream().cuda_stream
 
-def run(M, N, K, mode, resid_inplace, cg, bn, tma, iters=30):
+def run(M, N, K, mode, resid_inplace, cg, bn, tma, iters=30, stages=0):
+    check(lib, lib.parseq_set_option(None, b"gemm_stages", stages))
     check(lib, lib.parseq_set_option(None, b"cta_group", cg))
     check(lib, lib.parseq_set_option(None, b"block_n", bn))
     check(lib, lib.parseq_set_option(None, b"tma_epilogue", tma))
@@ -43,6 +44,12 @@ for K in (64, 384, 4096):
     for cg, bn, tma in [(1, 128, 1), (1, 256, 1)]:
         us, tf = run(M, 1536, K, 1, False, cg, bn, tma, iters=15)
         print(f"K={K:5d} cg={cg} bn={bn:3d} tma={tma} | {us:8.1f} us {tf:7.1f} TF/s")
+print("--- operand-ring depth sweep (gemm_stages cap; full ring: bn256 -> 4, bn192 -> 4, bn128 -> 6)")
+for name, N, K, mode, ri in cases:
+    for bn, depths in ((256, (2, 3, 4)), (128, (2, 3, 4, 6))):
+        for d in depths:
+            us, tf = run(M, N, K, mode, ri, 1, bn, 1, stages=d)
+            print(f"{name:5s} bn={bn:3d} stages={d} | {us:8.1f} us {tf:7.1f} TF/s")
 print("--- cuBLAS reference (torch.matmul bf16, no epilogue)")
 for N, K in ((1152, 384), (384, 384), (1536, 384), (384, 1536), (1536, 4096)):
     A = torch.randn((M, K), device="cuda").bfloat16(); W = torch.randn((N, K), device="cuda").bfloat16()

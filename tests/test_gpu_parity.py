@@ -51,7 +51,7 @@ def _decisions_ok(engine_logits, ref_logits, tau):
     return bool(same[clear].all()), int(clear.sum()), int(clear.numel())
 
 
-CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if not os.path.basename(p).startswith("filtered"))
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if not os.path.basename(p).startswith(("filtered", "vitstr")))
 
 
 @pytest.mark.parametrize("path", CASES, ids=lambda p: os.path.basename(p)[:-3])
