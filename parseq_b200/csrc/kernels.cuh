@@ -274,18 +274,19 @@ __global__ void __launch_bounds__(256, 2) enc_attention_any_kernel(const __nv_bf
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ld = 3ll * D;
   const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * ld + h * ATT_DH;
-  auto load_tile = [&](__nv_bfloat16* dst, int mat, int row0) {   // rows clamped to T-1 (masked later)
-    for (int i = tid; i < ATT_T * 8; i += 256) {
+  auto load_tile = [&](__nv_bfloat16* dst, int mat, int row0, int nrows) {   // rows clamped to T-1 (masked later)
+    for (int i = tid; i < nrows * 8; i += 256) {
       const int r = i >> 3, ck = i & 7;
       int row = row0 + r;
       if (row >= T) row = T - 1;
       cp_async_16(smem_u32(dst + att_swz(r, ck * 8)), base + static_cast<long long>(row) * ld + mat * D + ck * 8);
     }
   };
-  load_tile(sQ, 0, q0);
+  load_tile(sQ, 0, q0, ATT_T);
   cp_async_wait_all();
   __syncthreads();
   const int r0 = warp * 16;
+  const bool active = (q0 + r0) < T;     // warp-uniform: a warp whose 16 query rows are all padding only helps loading
   uint32_t qf[4][4];
 #pragma unroll
   for (int kt = 0; kt < 4; ++kt) {
@@ -302,10 +303,14 @@ __global__ void __launch_bounds__(256, 2) enc_attention_any_kernel(const __nv_bf
   for (int pass = 0; pass < 2; ++pass) {
     for (int kb = 0; kb < nkb; ++kb) {
       __syncthreads();                                       // previous tile fully consumed
-      load_tile(sK, 1, kb * ATT_T);
-      if (pass == 1) load_tile(sV, 2, kb * ATT_T);
+      // only the 16-key groups that hold at least one real key are loaded and multiplied (T = 129: 1 of 8 in block 1)
+      const int nvalid = (T - kb * ATT_T < ATT_T) ? (T - kb * ATT_T) : ATT_T;
+      const int np_max = (nvalid + 15) >> 4;
+      load_tile(sK, 1, kb * ATT_T, np_max * 16);
+      if (pass == 1) load_tile(sV, 2, kb * ATT_T, np_max * 16);
       cp_async_wait_all();
       __syncthreads();
+      if (!active) continue;
       float sacc[16][4];
 #pragma unroll
       for (int nt = 0; nt < 16; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(256, 2) enc_attention_any_kernel(const __nv_bf
       for (int kt = 0; kt < 4; ++kt) {
 #pragma unroll
         for (int np = 0; np < 8; ++np) {
+          if (np >= np_max) break;
           const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
           const int col = kt * 16 + ((lane >> 3) & 1) * 8;
           uint32_t b0, b1, b2, b3;
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(256, 2) enc_attention_any_kernel(const __nv_bf
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+          if (kk >= np_max) break;           // P is exactly 0 on the padded keys
           const uint32_t a0 = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
           const uint32_t a1 = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
           const uint32_t a2 = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
@@ -403,130 +410,6 @@ __global__ void build_ctx_rows_kernel(const float* __restrict__ emb, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// Decoder self-attention (query stream; DecoderLayer.forward_stream step 1, modules.py:69-72) for
-// head dim 32: one CTA per (image, query), one warp per head, lane = channel inside the head.
-//   q      : Qs[qpos] fp32 (W_q LN_q(pos_queries[qpos]) + b, pre-scaled by 1/sqrt(32); input independent)
-//   K/V    : kvtab[(k*V + ids[b,k]) * 2D + {0, D} + c] bf16   (content stream is a function of
-//            (position, token) only at decoder depth 1)
-//   mask   : mode 0 (AR step / NAR): keys 0..nkeys-1 all visible (model.py:130-136: the sliced
-//            causal row is all-False);  mode 1 (cloze refine): key k masked iff k == q+1 or an EOS
-//            occurs in ids[b, 0..k] (model.py:157,163)
-// out bf16 [B*nq, D] (A operand of the out-projection GEMM).
-__global__ void dec_self_attn_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
-                                     const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
-                                     int mode, int eos_id, __nv_bfloat16* __restrict__ out) {
-  grid_dep_launch();
-  grid_dep_wait();
-  const int b = blockIdx.x / nq, qi = blockIdx.x % nq;
-  const int qpos = q0 + qi;
-  const int c = threadIdx.x;             // channel; blockDim.x == D
-  const int lane = threadIdx.x & 31;
-  __shared__ int s_ids[32];
-  __shared__ int s_first_eos;
-  if (threadIdx.x < 32) {
-    int id = (threadIdx.x < nkeys) ? ids[static_cast<long long>(b) * ids_ld + threadIdx.x] : -1;
-    s_ids[threadIdx.x] = id;
-    const unsigned m = __ballot_sync(0xffffffffu, id == eos_id);
-    if (threadIdx.x == 0) s_first_eos = (m != 0u) ? (__ffs(m) - 1) : 1 << 30;
-  }
-  __syncthreads();
-  const float q = Qs[static_cast<long long>(qpos) * D + c];
-  const int first_eos = s_first_eos;
-  float my_s = -INFINITY;                // lane k keeps the score of key k
-  for (int k = 0; k < nkeys; ++k) {
-    const __nv_bfloat16* kr = kvtab + (static_cast<long long>(k) * V + s_ids[k]) * 2 * D;
-    float part = q * __bfloat162float(kr[c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const bool masked = (mode == 1) && (k == qpos + 1 || k >= first_eos);
-    if (lane == k) my_s = masked ? -INFINITY : part;
-  }
-  float mx = my_s;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = (lane < nkeys) ? expf(my_s - mx) : 0.f;   // exp(-inf)=0 for masked keys
-  float sum = e;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float pme = e / sum;
-  float acc = 0.f;
-  for (int k = 0; k < nkeys; ++k) {
-    const float pk = __shfl_sync(0xffffffffu, pme, k);
-    const __nv_bfloat16* vr = kvtab + (static_cast<long long>(k) * V + s_ids[k]) * 2 * D + D;
-    acc += pk * __bfloat162float(vr[c]);
-  }
-  out[static_cast<long long>(blockIdx.x) * D + c] = __float2bfloat16_rn(acc);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Decoder cross-attention (forward_stream step 2, modules.py:74-75) over the per-image K/V cache
-// kv bf16 [B, T, 2D] (K cols [0,D), V cols [D,2D)); q fp32 [B*nq, D] already scaled by 1/sqrt(32).
-// One CTA per (image, query), one warp per head: scores with lane = key (each lane dots one
-// 32-wide key row), softmax across the warp, then lane = channel for P.V.  No mask.
-template <int MAXT>
-__global__ void dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv, int T, int D,
-                                      int nq, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float s_cross[];     // [heads][32] q  +  [heads][MAXT] p
-  const int heads = blockDim.x >> 5;
-  float* s_q = s_cross;
-  float* s_p = s_cross + heads * 32;
-  const int b = blockIdx.x / nq;
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = threadIdx.x;
-  s_q[c] = q[static_cast<long long>(blockIdx.x) * D + c];
-  __syncwarp();
-  const __nv_bfloat16* kvb = kv + static_cast<long long>(b) * T * 2 * D;
-  constexpr int R = MAXT / 32;
-  float sc[R];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int t = r * 32 + lane;
-    float s = -INFINITY;
-    if (t < T) {
-      const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + h * 32);
-      s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = __ldg(kr + j);
-        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(p2[e]);
-          s += s_q[h * 32 + j * 8 + e * 2] * f.x;
-          s += s_q[h * 32 + j * 8 + e * 2 + 1] * f.y;
-        }
-      }
-    }
-    sc[r] = s;
-    mx = fmaxf(mx, s);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int t = r * 32 + lane;
-    const float e = (t < T) ? expf(sc[r] - mx) : 0.f;
-    sc[r] = e;
-    sum += e;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float inv = 1.0f / sum;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int t = r * 32 + lane;
-    if (t < T) s_p[h * MAXT + t] = sc[r] * inv;
-  }
-  __syncwarp();
-  float acc = 0.f;
-  const __nv_bfloat16* vb = kvb + D + c;
-  for (int t = 0; t < T; ++t) acc += s_p[h * MAXT + t] * __bfloat162float(vb[static_cast<long long>(t) * 2 * D]);
-  out[static_cast<long long>(blockIdx.x) * D + c] = __float2bfloat16_rn(acc);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Greedy argmax (first maximum wins, torch.argmax semantics) of logits rows -> token ids.
 // One warp per row.  Row r = (b, s): reads logits[b, src_pos0 + s, :C], writes ids[b*ids_ld + dst_pos0 + s].
 // If `forced` != nullptr the written id is forced[b*forced_ld + dst_pos0 + s] (teacher forcing).
@@ -565,10 +448,6 @@ __global__ void fill_ids_kernel(int* __restrict__ ids, int B, int ld, int bos, i
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * ld) ids[i] = ((i % ld) == 0) ? bos : pad;
 }
-__global__ void copy_ids_kernel(const int* __restrict__ src, int src_ld, int* __restrict__ dst, int dst_ld, int B, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B * n) dst[static_cast<long long>(i / n) * dst_ld + (i % n)] = src[static_cast<long long>(i / n) * src_ld + (i % n)];
-}
 
 // S = number of AR steps the reference returns under its batch-wide early exit (model.py:144):
 // smallest j>=1 such that every row has an EOS among ids[b,1..j]  == max_b first_eos_pos(b); L if any row has none.
@@ -591,8 +470,15 @@ __global__ void set_int_kernel(int* p, int v) {
 // ---------------------------------------------------------------------------------------------
 // Decoder self-attention, one CTA per image, one warp per head (head dim 32), ALL nq queries of the pass:
 // the context K rows (lane = key, <= 32 keys) and V columns (lane = channel) of the head are gathered once from the
-// (position, token) table into registers, then every query costs ~130 warp instructions.  Same semantics as
-// dec_self_attn_kernel (kept for reference / tests).
+// (position, token) table into registers, then every query costs ~130 warp instructions.
+// (DecoderLayer.forward_stream step 1, modules.py:69-72)
+//   q      : Qs[qpos] fp32 (W_q LN_q(pos_queries[qpos]) + b, pre-scaled by 1/sqrt(32); input independent)
+//   K/V    : kvtab[(k*V + ids[b,k]) * 2D + {0, D} + c] bf16   (the content stream is a function of
+//            (position, token) only at decoder depth 1)
+//   mask   : mode 0 (AR step / NAR): keys 0..nkeys-1 all visible (model.py:130-136: the sliced causal row is
+//            all-False);  mode 1 (cloze refine): key k masked iff k == q+1 or an EOS occurs in ids[b, 0..k]
+//            (model.py:157,163)
+// out bf16 [B*nq, D] (A operand of the out-projection GEMM).
 __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
                                       const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
                                       int mode, int eos_id, __nv_bfloat16* __restrict__ out, int qsplit) {

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/ -m gpu -q -x --timeout 600 2>&1 | tail -6
+timeout 300 python tests/bench_vitstr.py 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu-baseline 2>gpurun_out/bench.err | tee gpurun_out/bench_last.json | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print(d['value'], 'img/s', d['ms_per_step'], 'ms/step | e2e', d['e2e']['value'], '| e2e_u8', d.get('e2e_u8', {}).get('value'), '| roofline', d['roofline'])"
+tail -2 gpurun_out/bench.err
+timeout 300 python tests/bench_gemm.py 65536 2>&1 | head -18

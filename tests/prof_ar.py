@@ -14,6 +14,6 @@ with torch.inference_mode():
 torch.cuda.synchronize()
 prof = m.model.engine().get_ar_profile()
 names = ["P1 self", "bar", "P2 oproj", "bar", "P3 ln+q", "bar", "P4 cross", "bar", "P5 oproj", "bar", "P6 ln+l1", "bar", "P7 l2", "bar", "P8 head"]
-for step in (1, 12, 25):
+for step in (1, 12, 13, 25):
     t = prof[step]
     print(f"step {step}: " + "  ".join(f"{names[k]}={(t[k+1]-t[k])/1000:.1f}" for k in range(15)), f" | total {(t[15]-t[0])/1000:.1f} us")
