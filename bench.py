@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--dec-chunk", type=int, default=0, help="images per decoder chain (0 = engine default 128)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-fuse-ln", action="store_true", help="separate LayerNorm kernels instead of the fused residual-GEMM + LN")
     ap.add_argument("--attn-impl", type=int, default=-1, help="encoder attention: 1 tcgen05 (default), 0 mma.sync")
     ap.add_argument("--no-ar-kernel", action="store_true", help="AR loop as separate kernels instead of the persistent kernel")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM tile: 0 auto, 1 single CTA, 2 CTA pair")
@@ -227,6 +228,8 @@ def main():
         model.model.set_engine_option("attn_impl", args.attn_impl)
     if args.no_ar_kernel:
         model.model.set_engine_option("ar_kernel", 0)
+    if args.no_fuse_ln:
+        model.model.set_engine_option("fuse_ln", 0)
     if args.cta_group:
         model.model.set_engine_option("cta_group", args.cta_group)
     if args.block_n:

@@ -124,7 +124,8 @@ int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count
 /* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per encoder pass inside a
  * super-chunk), "dec_chunk" (images per decoder chain; the chains of a super-chunk run concurrently on their own
  * streams), "use_graph" (0/1), "pdl" (programmatic dependent launch, 0/1), "timing" (1: record a CUDA-event pair around every launch
- * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests). */
+ * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests), "fuse_ln" (1: the attention-projection / fc2 GEMMs also
+ * produce the following LayerNorm, default; 0: separate LayerNorm kernels). */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of
  * category 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other. */
@@ -142,6 +143,12 @@ const char* parseq_version(void);
 int parseq_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                      int M, int N, int K, int mode, float alpha, const float* resid, int64_t ldr,
                      int resid_mod, void* out, int64_t ldo, parseq_stream_t stream);
+/* Residual GEMM fused with the LayerNorm that follows it (timm Block: x = x + proj(attn) ; norm2(x) and
+ * x = x + fc2(..) ; next norm1(x)):  x_inout[M, D] += A[M, K] * W[D, K]^T + bias (fp32, in place),
+ * xn_bf16[M, D] = bf16(LayerNorm(x_inout; gamma, beta, eps)).  D in {192, 384}. */
+int parseq_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                        int M, int D, int K, float* x_inout, const float* gamma, const float* beta,
+                        float eps, void* xn_bf16, parseq_stream_t stream);
 /* y = bf16(LayerNorm(x; gamma, beta, eps)), x fp32 [M, D]. */
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M,
                           int D, void* y_bf16, float* y_f32_or_null, parseq_stream_t stream);

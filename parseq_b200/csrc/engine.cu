@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "dec_ar.cuh"
 #include "attn_tc.cuh"
+#include "gemm_ln.cuh"
 
 namespace {
 
@@ -177,6 +178,8 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384>::kSmemBytes));
   PQ_TRY((warm_gemm_cfg<64, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 1>()));
   PQ_TRY((warm_gemm_cfg<192, 1>()));
@@ -245,6 +248,43 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
   if (BN == 192) return launch_gemm_cfg<192, 1>(ta, tb, tc, p, tiles, st);
   if (BN == 64) return launch_gemm_cfg<64, 1>(ta, tb, tc, p, tiles, st);
   return launch_gemm_cfg<128, 1>(ta, tb, tc, p, tiles, st);
+}
+
+// x[M, D] += A[M, K] * W[D, K]^T + bias (fp32, in place); xn[M, D] = bf16(LayerNorm(x; gamma, beta, eps))   (gemm_ln.cuh)
+bool gemm_ln_supported(int D) { return D == 192 || D == 384; }
+template <int D>
+int launch_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int K, float* x,
+                   const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
+  using Cfg = pq::GemmLnCfg<D>;
+  auto kern = pq::gemm_ln_fused_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb, tx, tn;
+  PQ_TRY(make_tmap(&ta, A, 2, M, K, lda, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
+  PQ_TRY(make_tmap(&tb, W, 2, D, K, ldw, pq::GEMM_BLOCK_K, Cfg::kNH));
+  PQ_TRY(make_tmap(&tx, x, 4, M, D, D, 32, 32));
+  PQ_TRY(make_tmap(&tn, xn, 2, M, D, D, 64, 32));
+  pq::GemmLnParams p;
+  p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
+  const int grid = p.num_m_tiles < g_sm_count ? p.num_m_tiles : g_sm_count;
+  return launch_k(kern, dim3(grid), dim3(pq::GLN_THREADS), Cfg::kSmemBytes, st, ta, tb, tx, tn, p);
+}
+int gemm_ln_launch(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int D, int K,
+                   float* x, const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
+  if (M <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm_ln: empty problem");
+  if (g_sm_count == 0) {
+    int dev = 0;
+    PQ_CUDA(cudaGetDevice(&dev));
+    PQ_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  PQ_TRY(load_driver_api());
+  if (D == 384) return launch_gemm_ln<384>(A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  if (D == 192) return launch_gemm_ln<192>(A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  return fail(PARSEQ_ERR_UNSUPPORTED, "gemm_ln: embed_dim must be 192 or 384 (full rows in 512 TMEM columns)");
 }
 
 int layernorm_launch(const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
@@ -322,6 +362,7 @@ struct parseq_engine {
   int dec_chunk = 128;              // images per decoder chain (each chain runs on its own stream)
   // persistent AR-loop kernel state (whole super-chunk)
   bool use_ar_kernel = true;
+  bool fuse_ln = true;              // residual GEMMs (attn.proj, mlp.fc2) produce the following LayerNorm too (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
   float *ar_y = nullptr, *ar_qc = nullptr, *ar_part = nullptr;
   int* ar_ids = nullptr;
@@ -471,6 +512,13 @@ int gemm(parseq_engine* e, const void* A, long long lda, const void* W, long lon
   TimedScope ts(e, st, e->cur_cat == CAT_DEC_GEMM ? CAT_DEC_GEMM : CAT_ENC_GEMM, 2.0 * M * N * K);
   return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st);
 }
+// x += A W^T + b;  y = bf16(LayerNorm(x; <ln_prefix>))  in one kernel
+int gemm_ln(parseq_engine* e, const void* A, long long lda, const std::string& lin, int M, int K, float* x,
+            const std::string& ln_prefix, float eps, void* y, cudaStream_t st) {
+  TimedScope ts(e, st, CAT_ENC_GEMM, 2.0 * M * e->D * K);
+  return gemm_ln_launch(A, lda, e->w(lin + ".weight"), K, e->wf(lin + ".bias"), M, e->D, K, x, e->wf(ln_prefix + ".weight"),
+                        e->wf(ln_prefix + ".bias"), eps, y, st);
+}
 int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float eps, int M, void* y, float* y32,
               cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   TimedScope ts(e, st, CAT_LN, 0.0);
@@ -515,23 +563,42 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
                     reinterpret_cast<const float4*>(e->wf("encoder.pos_embed")), reinterpret_cast<float4*>(e->x), B, e->Tp,
                     D / 4));
   }
+  // With fuse_ln the two residual GEMMs of a block also emit the LayerNorm that consumes their result (norm2 after
+  // attn.proj; the next block's norm1 - or the final encoder.norm - after mlp.fc2): the fp32 residual stream is read
+  // and written once per GEMM instead of once more per LayerNorm.
+  const bool fuse = e->fuse_ln && gemm_ln_supported(D);
+  bool final_done = false;
   for (int i = 0; i < e->cfg.enc_depth; ++i) {
     const std::string p = "encoder.blocks." + std::to_string(i) + ".";
-    PQ_TRY(layernorm(e, e->x, p + "norm1", 1e-6f, M, e->xn, nullptr, st));
+    const bool last = (i == e->cfg.enc_depth - 1);
+    if (!(fuse && i > 0)) PQ_TRY(layernorm(e, e->x, p + "norm1", 1e-6f, M, e->xn, nullptr, st));
     PQ_TRY(gemm(e, e->xn, D, e->w(p + "attn.qkv.weight"), D, e->wf(p + "attn.qkv.bias"), M, 3 * D, D, pq::EPI_BF16,
                 1.0f, nullptr, 0, 0, e->qkv, 3 * D, st));
     {
       TimedScope ts(e, st, CAT_ENC_ATTN, 4.0 * B * T * T * D);
       PQ_TRY(enc_attention_launch(e->qkv, B, T, D, e->cfg.enc_num_heads, e->att, st));
     }
-    PQ_TRY(gemm(e, e->att, D, e->w(p + "attn.proj.weight"), D, e->wf(p + "attn.proj.bias"), M, D, D, pq::EPI_F32, 1.0f,
-                e->x, D, 0, e->x, D, st));
-    PQ_TRY(layernorm(e, e->x, p + "norm2", 1e-6f, M, e->xn, nullptr, st));
+    if (fuse) {
+      PQ_TRY(gemm_ln(e, e->att, D, p + "attn.proj", M, D, e->x, p + "norm2", 1e-6f, e->xn, st));
+    } else {
+      PQ_TRY(gemm(e, e->att, D, e->w(p + "attn.proj.weight"), D, e->wf(p + "attn.proj.bias"), M, D, D, pq::EPI_F32, 1.0f,
+                  e->x, D, 0, e->x, D, st));
+      PQ_TRY(layernorm(e, e->x, p + "norm2", 1e-6f, M, e->xn, nullptr, st));
+    }
     PQ_TRY(gemm(e, e->xn, D, e->w(p + "mlp.fc1.weight"), D, e->wf(p + "mlp.fc1.bias"), M, e->Me, D, pq::EPI_GELU_BF16,
                 1.0f, nullptr, 0, 0, e->hid, e->Me, st));
-    PQ_TRY(gemm(e, e->hid, e->Me, e->w(p + "mlp.fc2.weight"), e->Me, e->wf(p + "mlp.fc2.bias"), M, D, e->Me,
-                pq::EPI_F32, 1.0f, e->x, D, 0, e->x, D, st));
+    if (fuse && !last) {
+      PQ_TRY(gemm_ln(e, e->hid, e->Me, p + "mlp.fc2", M, e->Me, e->x, "encoder.blocks." + std::to_string(i + 1) + ".norm1",
+                     1e-6f, e->xn, st));
+    } else if (fuse && final_norm && memory32 == nullptr) {
+      PQ_TRY(gemm_ln(e, e->hid, e->Me, p + "mlp.fc2", M, e->Me, e->x, "encoder.norm", 1e-6f, mem_out, st));
+      final_done = true;
+    } else {
+      PQ_TRY(gemm(e, e->hid, e->Me, e->w(p + "mlp.fc2.weight"), e->Me, e->wf(p + "mlp.fc2.bias"), M, D, e->Me,
+                  pq::EPI_F32, 1.0f, e->x, D, 0, e->x, D, st));
+    }
   }
+  if (final_done) return PARSEQ_OK;
   if (final_norm) PQ_TRY(layernorm(e, e->x, "encoder.norm", 1e-6f, M, mem_out, memory32, st));
   return PARSEQ_OK;
 }
@@ -1172,6 +1239,12 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (n == "attn_impl") { g_attn_impl = value != 0 ? 1 : 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "pdl") { g_use_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
+  if (n == "fuse_ln") {
+    if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
+    e->fuse_ln = value != 0;
+    drop_graphs(e);
+    return PARSEQ_OK;
+  }
   if (n == "gemm_stages") { g_gemm_stages = value > 0 ? static_cast<int>(value) : 0; return PARSEQ_OK; }
   if (n == "cta_group") {
     if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "cta_group: 0 (auto) / 1 / 2");
@@ -1233,6 +1306,11 @@ int parseq_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, con
   if (mode < 0 || mode > 2) return fail(PARSEQ_ERR_INVALID_ARG, "bad epilogue mode");
   return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo,
                      reinterpret_cast<cudaStream_t>(stream));
+}
+int parseq_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int D, int K,
+                         float* x_inout, const float* gamma, const float* beta, float eps, void* xn_bf16,
+                         parseq_stream_t stream) {
+  return gemm_ln_launch(A, lda, W, ldw, bias, M, D, K, x_inout, gamma, beta, eps, xn_bf16, reinterpret_cast<cudaStream_t>(stream));
 }
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y_bf16,
                           float* y_f32_or_null, parseq_stream_t stream) {

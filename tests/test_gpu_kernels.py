@@ -140,6 +140,69 @@ def test_gemm_head_layout(lib):
     assert logits.abs().max().item() == 0.0       # nothing written outside the step's rows
 
 
+def _gemm_ln(lib, A, W, bias, x, gamma, beta, eps):
+    from parseq_b200.engine import check
+    M, K = A.shape
+    D = W.shape[0]
+    xn = torch.empty((M, D), dtype=torch.bfloat16, device=A.device)
+    check(lib, lib.parseq_gemm_ln_bf16(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), bias.data_ptr(), M, D, K,
+                                       x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, xn.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    return xn
+
+
+@pytest.mark.parametrize("M,D,K", [(128, 384, 384), (300, 384, 384), (4096, 384, 1536), (77, 384, 1536),
+                                   (148 * 128 * 2 + 77, 384, 384), (65536, 384, 1536), (513, 192, 192), (2000, 192, 768)])
+def test_gemm_ln_fused(lib, M, D, K):
+    """x += A W^T + b (fp32 in place) and xn = bf16(LayerNorm(x)) in one kernel (gemm_ln.cuh) vs the same two ops in torch;
+    ragged M, several tiles per CTA, both K of the encoder (attn.proj, mlp.fc2)."""
+    g = torch.Generator(device="cuda").manual_seed(M + D + K)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((D, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((D,), device="cuda", generator=g)
+    gamma = 1.0 + 0.1 * torch.randn((D,), device="cuda", generator=g)
+    beta = 0.05 * torch.randn((D,), device="cuda", generator=g)
+    x0 = torch.randn((M, D), device="cuda", generator=g) + 0.3 * torch.randn((M, 1), device="cuda", generator=g)
+    x = x0.clone()
+    xn = _gemm_ln(lib, A, W, bias, x, gamma, beta, 1e-6)
+    ref_x = x0 + (A.float() @ W.float().t() + bias)
+    errx = (x - ref_x).abs().max().item()
+    assert errx <= 2e-4 * max(1.0, ref_x.abs().max().item()), ("x", errx)
+    # the LayerNorm half is checked on the kernel's own x (isolates it from the GEMM summation order)
+    ref_n = torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-6)
+    errn = (xn.float() - ref_n).abs()
+    assert (errn <= 2.0 ** -8 * ref_n.abs() + 1e-5).all(), ("xn", errn.max().item())       # one bf16 rounding
+    same = (xn == ref_n.bfloat16()).float().mean().item()
+    assert same > 0.995, same                                                               # ties at rounding boundaries only
+    x2 = x0.clone()
+    xn2 = _gemm_ln(lib, A, W, bias, x2, gamma, beta, 1e-6)
+    assert torch.equal(x, x2) and torch.equal(xn, xn2)                                       # deterministic
+
+
+def test_gemm_ln_fused_matches_unfused_pair(lib):
+    """Same rounding points as the TMA reduce-add GEMM epilogue followed by layernorm_kernel: x bit-identical."""
+    from parseq_b200.engine import check
+    M, D, K = 3000, 384, 1536
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((D, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((D,), device="cuda", generator=g)
+    gamma = 1.0 + 0.1 * torch.randn((D,), device="cuda", generator=g)
+    beta = 0.05 * torch.randn((D,), device="cuda", generator=g)
+    x0 = torch.randn((M, D), device="cuda", generator=g)
+    xa = x0.clone()
+    xna = _gemm_ln(lib, A, W, bias, xa, gamma, beta, 1e-6)
+    xb = x0.clone()
+    _gemm(lib, A, W, bias, 0, resid=xb, out=xb)
+    xnb = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+    check(lib, lib.parseq_layernorm_bf16(xb.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-6, M, D, xnb.data_ptr(), None,
+                                         _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb)
+    assert (xna == xnb).float().mean().item() > 0.999
+    assert (xna.float() - xnb.float()).abs().max().item() <= 2.0 ** -7 * xnb.float().abs().max().item()
+
+
 @pytest.mark.parametrize("D,eps", [(192, 1e-6), (384, 1e-6), (384, 1e-5), (768, 1e-5)])
 def test_layernorm(lib, D, eps):
     from parseq_b200.engine import check
