@@ -124,11 +124,13 @@ int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count
 /* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per encoder pass inside a
  * super-chunk), "dec_chunk" (images per decoder chain; the chains of a super-chunk run concurrently on their own
  * streams), "use_graph" (0/1), "pdl" (programmatic dependent launch, 0/1), "timing" (1: record a CUDA-event pair around every launch
- * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests), "fuse_ln" (1: the attention-projection / fc2 GEMMs also
- * produce the following LayerNorm, default; 0: separate LayerNorm kernels). */
+ * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests), "fuse_ln" (bit 0: the attention-projection GEMM, bit 1: the fc2 GEMM
+ * also produces the LayerNorm that follows it, used when the batch fills the machine at least twice with 128-row tiles; bit 2:
+ * for any batch; default 3; 0: separate LayerNorm kernels). */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of
- * category 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other. */
+ * category 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other,
+ * 6 encoder residual GEMM fused with LayerNorm. */
 int parseq_get_timing(parseq_engine* e, int category, double* ms, double* flops, int64_t* count);
 /* Debug: after a forward with option "ar_prof"=1, copies the [32 steps][16 slots] globaltimer (ns) stamps that block 0 of
  * the persistent AR kernel recorded at its phase boundaries. */

@@ -362,7 +362,7 @@ struct parseq_engine {
   int dec_chunk = 128;              // images per decoder chain (each chain runs on its own stream)
   // persistent AR-loop kernel state (whole super-chunk)
   bool use_ar_kernel = true;
-  bool fuse_ln = true;              // residual GEMMs (attn.proj, mlp.fc2) produce the following LayerNorm too (gemm_ln.cuh)
+  int fuse_ln = 3;                  // bit 0: attn.proj, bit 1: mlp.fc2 also produce the LayerNorm that follows (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
   float *ar_y = nullptr, *ar_qc = nullptr, *ar_part = nullptr;
   int* ar_ids = nullptr;
@@ -487,7 +487,8 @@ void free_workspace(parseq_engine* e) {
 }
 
 // categories: 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other
-enum { CAT_ENC_GEMM = 0, CAT_ENC_ATTN = 1, CAT_LN = 2, CAT_DEC_GEMM = 3, CAT_DEC_ATTN = 4, CAT_MISC = 5, CAT_COUNT = 6 };
+enum { CAT_ENC_GEMM = 0, CAT_ENC_ATTN = 1, CAT_LN = 2, CAT_DEC_GEMM = 3, CAT_DEC_ATTN = 4, CAT_MISC = 5, CAT_ENC_GEMM_LN = 6,
+       CAT_COUNT = 7 };
 
 cudaEvent_t pool_event(parseq_engine* e) {
   if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
@@ -515,7 +516,7 @@ int gemm(parseq_engine* e, const void* A, long long lda, const void* W, long lon
 // x += A W^T + b;  y = bf16(LayerNorm(x; <ln_prefix>))  in one kernel
 int gemm_ln(parseq_engine* e, const void* A, long long lda, const std::string& lin, int M, int K, float* x,
             const std::string& ln_prefix, float eps, void* y, cudaStream_t st) {
-  TimedScope ts(e, st, CAT_ENC_GEMM, 2.0 * M * e->D * K);
+  TimedScope ts(e, st, CAT_ENC_GEMM_LN, 2.0 * M * e->D * K);
   return gemm_ln_launch(A, lda, e->w(lin + ".weight"), K, e->wf(lin + ".bias"), M, e->D, K, x, e->wf(ln_prefix + ".weight"),
                         e->wf(ln_prefix + ".bias"), eps, y, st);
 }
@@ -566,19 +567,24 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
   // With fuse_ln the two residual GEMMs of a block also emit the LayerNorm that consumes their result (norm2 after
   // attn.proj; the next block's norm1 - or the final encoder.norm - after mlp.fc2): the fp32 residual stream is read
   // and written once per GEMM instead of once more per LayerNorm.
-  const bool fuse = e->fuse_ln && gemm_ln_supported(D);
+  // The fused kernel owns whole 128-row tiles (one CTA per tile, both column halves in sequence): it pays off once
+  // the tiles fill the machine about twice; below that the N-split GEMM + LayerNorm pair has the lower latency
+  // (bs=1: 1.67 ms vs 1.93 ms p50).  "fuse_ln" bit 2 forces it for any M (tests).
+  const bool big = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M >= 2 * g_sm_count || (e->fuse_ln & 4);
+  const bool fuse_proj = (e->fuse_ln & 1) && gemm_ln_supported(D) && big;
+  const bool fuse_fc2 = (e->fuse_ln & 2) && gemm_ln_supported(D) && big;
   bool final_done = false;
   for (int i = 0; i < e->cfg.enc_depth; ++i) {
     const std::string p = "encoder.blocks." + std::to_string(i) + ".";
     const bool last = (i == e->cfg.enc_depth - 1);
-    if (!(fuse && i > 0)) PQ_TRY(layernorm(e, e->x, p + "norm1", 1e-6f, M, e->xn, nullptr, st));
+    if (!(fuse_fc2 && i > 0)) PQ_TRY(layernorm(e, e->x, p + "norm1", 1e-6f, M, e->xn, nullptr, st));
     PQ_TRY(gemm(e, e->xn, D, e->w(p + "attn.qkv.weight"), D, e->wf(p + "attn.qkv.bias"), M, 3 * D, D, pq::EPI_BF16,
                 1.0f, nullptr, 0, 0, e->qkv, 3 * D, st));
     {
       TimedScope ts(e, st, CAT_ENC_ATTN, 4.0 * B * T * T * D);
       PQ_TRY(enc_attention_launch(e->qkv, B, T, D, e->cfg.enc_num_heads, e->att, st));
     }
-    if (fuse) {
+    if (fuse_proj) {
       PQ_TRY(gemm_ln(e, e->att, D, p + "attn.proj", M, D, e->x, p + "norm2", 1e-6f, e->xn, st));
     } else {
       PQ_TRY(gemm(e, e->att, D, e->w(p + "attn.proj.weight"), D, e->wf(p + "attn.proj.bias"), M, D, D, pq::EPI_F32, 1.0f,
@@ -587,10 +593,10 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
     }
     PQ_TRY(gemm(e, e->xn, D, e->w(p + "mlp.fc1.weight"), D, e->wf(p + "mlp.fc1.bias"), M, e->Me, D, pq::EPI_GELU_BF16,
                 1.0f, nullptr, 0, 0, e->hid, e->Me, st));
-    if (fuse && !last) {
+    if (fuse_fc2 && !last) {
       PQ_TRY(gemm_ln(e, e->hid, e->Me, p + "mlp.fc2", M, e->Me, e->x, "encoder.blocks." + std::to_string(i + 1) + ".norm1",
                      1e-6f, e->xn, st));
-    } else if (fuse && final_norm && memory32 == nullptr) {
+    } else if (fuse_fc2 && final_norm && memory32 == nullptr) {
       PQ_TRY(gemm_ln(e, e->hid, e->Me, p + "mlp.fc2", M, e->Me, e->x, "encoder.norm", 1e-6f, mem_out, st));
       final_done = true;
     } else {
@@ -1241,7 +1247,7 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
   if (n == "fuse_ln") {
     if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
-    e->fuse_ln = value != 0;
+    e->fuse_ln = static_cast<int>(value) & 7;
     drop_graphs(e);
     return PARSEQ_OK;
   }

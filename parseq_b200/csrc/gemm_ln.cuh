@@ -11,10 +11,11 @@
 //   warp 0      TMA producer (A tile 128x64 + a HALF of W: D/2 x 64 per stage; the two column halves of a tile are
 //               accumulated one after the other so that a stage stays 40 KB and shared memory is left for the epilogue)
 //   warp 1      MMA issuer (UMMA 128 x D/2 x 16 into TMEM columns [h*D/2, (h+1)*D/2)), TMEM alloc / dealloc
-//   warps 2..5  epilogue, one per TMEM lane quarter, thread = row:
-//       pass 1 (32-column chunks): x tile chunk arrives by TMA in a 128B-swizzled slab (6 slabs per warp are kept in
+//   warps 2..9  epilogue, two per TMEM lane quarter, thread = row, the two warps of a quarter take alternate chunks:
+//       pass 1 (32-column chunks): x tile chunk arrives by TMA in a 128B-swizzled slab (3 slabs per warp are kept in
 //               flight), v = (acc + bias) + x is written back in place and stored with TMA, written back to TMEM, and
 //               accumulated into the row's shifted sum / sum of squares; pass 1 of half 0 overlaps the MMAs of half 1;
+//       the two partial (mean, M2) of a row are combined through shared memory (Chan's parallel variance);
 //       pass 2 (64-column chunks): v is read back from TMEM, normalised, packed to bf16 and TMA-stored to xn.
 // Rounding points are those of the unfused pair (TMA reduce-add epilogue + layernorm_kernel): fp32 x, bf16 xn.
 #pragma once
@@ -31,9 +32,9 @@ struct GemmLnParams {
   int num_m_tiles;
 };
 
-constexpr int GLN_EPI_WARPS = 4;
+constexpr int GLN_EPI_WARPS = 8;
 constexpr int GLN_THREADS = 64 + 32 * GLN_EPI_WARPS;
-constexpr int GLN_SLABS = 6;          // x chunks in flight per epilogue warp
+constexpr int GLN_SLABS = 3;          // x chunks in flight per epilogue warp
 
 template <int D>
 struct GemmLnCfg {
@@ -42,7 +43,7 @@ struct GemmLnCfg {
   static constexpr int kBBytes = kNH * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabBytes = GLN_EPI_WARPS * GLN_SLABS * 4096;
-  static constexpr int kParamBytes = 3 * D * 4;                       // bias, gamma, beta
+  static constexpr int kParamBytes = 3 * D * 4 + 4 * 2 * 32 * 8;      // bias, gamma, beta; (mean, M2) exchange of the warp pairs
   static constexpr int kBarBytes = 512;
   static constexpr int kStagesRaw = (232448 - 1024 - kBarBytes - kSlabBytes - kParamBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
@@ -52,8 +53,9 @@ struct GemmLnCfg {
   static_assert(kNH % 16 == 0 && kNH <= 256, "UMMA N");
   static_assert(kBBytes % 1024 == 0 && kStageBytes % 1024 == 0, "1024-B aligned operand tiles");
   static_assert(kStages >= 3, "pipeline depth");
-  static constexpr int kRounds = kChunks / GLN_SLABS;                 // phases every slab barrier completes per tile
-  static_assert(kChunks % GLN_SLABS == 0, "whole rounds of slabs per tile");
+  static constexpr int kMyChunks = kChunks / 2;                       // pass-1 chunks per epilogue warp
+  static constexpr int kRounds = kMyChunks / GLN_SLABS;               // phases every slab barrier completes per tile
+  static_assert(kMyChunks % GLN_SLABS == 0, "whole rounds of slabs per tile");
 };
 
 template <int D>
@@ -70,11 +72,12 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   float* s_bias = reinterpret_cast<float*>(slab_base + Cfg::kSlabBytes);
   float* s_gamma = s_bias + D;
   float* s_beta = s_gamma + D;
+  float2* s_stat = reinterpret_cast<float2*>(s_beta + D);             // [4 quarters][2 warps][32 rows] (mean, M2)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(slab_base + Cfg::kSlabBytes + Cfg::kParamBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;      // [2]: accumulator half h complete
-  uint64_t* tempty_bar = tfull_bar + 2;                // [1]: the epilogue is done with this tile's TMEM
-  uint64_t* x_bar = tempty_bar + 1;                    // [GLN_EPI_WARPS][GLN_SLABS]: x chunk landed
+  uint64_t* tempty_bar = tfull_bar + 2;                // [2]: the epilogue is done with TMEM column half h of this tile
+  uint64_t* x_bar = tempty_bar + 2;                    // [GLN_EPI_WARPS][GLN_SLABS]: x chunk landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + GLN_EPI_WARPS * GLN_SLABS);
 
   const int warp = threadIdx.x >> 5;
@@ -88,6 +91,7 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], GLN_EPI_WARPS);
+    mbar_init(&tempty_bar[1], GLN_EPI_WARPS);
     for (int i = 0; i < GLN_EPI_WARPS * GLN_SLABS; ++i) mbar_init(&x_bar[i], 1);
     fence_mbar_init();
   }
@@ -130,9 +134,11 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[0], tphase ^ 1u);        // previous tile's rows have left TMEM
-        tc_fence_after();
         for (int h = 0; h < 2; ++h) {
+          // the previous tile's rows have left this half of TMEM (pass 2 releases the low columns first, so the
+          // MMAs of half 0 overlap the rest of the previous tile's pass 2)
+          mbar_wait(&tempty_bar[h], tphase ^ 1u);
+          tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(h * Cfg::kNH);
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
@@ -153,9 +159,10 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue: thread = row =====================
+    // ===================== epilogue: thread = row; warp pair (w = 0, 1) of a quarter alternates chunks =====================
     const int quarter = warp & 3;
     const int ew = warp - 2;
+    const int w = ew >> 2;
     uint8_t* my_slabs = slab_base + ew * (GLN_SLABS * 4096);
     uint64_t* my_xbar = x_bar + ew * GLN_SLABS;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -167,20 +174,27 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // every slab is free here (first tile, or bulk_wait_group_read<0> at the end of the previous tile)
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < GLN_SLABS; ++c) {
-          mbar_expect_tx(&my_xbar[c], 4096);
-          tma_load_2d(my_slabs + c * 4096, &tmX, &my_xbar[c], c * 32, row0);
+        for (int i = 0; i < GLN_SLABS; ++i) {
+          mbar_expect_tx(&my_xbar[i], 4096);
+          tma_load_2d(my_slabs + i * 4096, &tmX, &my_xbar[i], (2 * i + w) * 32, row0);
         }
       }
       float shift = 0.f, sum = 0.f, sq = 0.f;
+      bool half1_ready = false;
 #pragma unroll 1
-      for (int c = 0; c < Cfg::kChunks; ++c) {
-        if (c == 0 || c == Cfg::kChunks / 2) {         // accumulator half ready (pass 1 of half 0 overlaps half 1's MMAs)
-          mbar_wait(&tfull_bar[c == 0 ? 0 : 1], tphase);
+      for (int i = 0; i < Cfg::kMyChunks; ++i) {
+        const int c = 2 * i + w;                       // this warp's i-th 32-column chunk
+        if (i == 0) {                                  // accumulator half 0 ready
+          mbar_wait(&tfull_bar[0], tphase);
           tc_fence_after();
         }
-        const int s = c % GLN_SLABS;
-        mbar_wait(&my_xbar[s], (xround + static_cast<uint32_t>(c / GLN_SLABS)) & 1u);
+        if (c >= Cfg::kChunks / 2 && !half1_ready) {   // pass 1 of half 0 overlapped half 1's MMAs
+          mbar_wait(&tfull_bar[1], tphase);
+          tc_fence_after();
+          half1_ready = true;
+        }
+        const int s = i % GLN_SLABS;
+        mbar_wait(&my_xbar[s], (xround + static_cast<uint32_t>(i / GLN_SLABS)) & 1u);
         uint32_t v[32];
         tmem_ld_32x32b_x32(trow + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
@@ -197,7 +211,7 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           r.z = (__uint_as_float(v[jj * 4 + 2]) + bb[jj * 4 + 2]) + xo.z;
           r.w = (__uint_as_float(v[jj * 4 + 3]) + bb[jj * 4 + 3]) + xo.w;
           *px = r;
-          if (c == 0 && jj == 0) shift = r.x;          // shifted single-pass variance (shift = first element of the row)
+          if (i == 0 && jj == 0) shift = r.x;          // shifted single-pass variance (shift = first element seen)
           const float d0 = r.x - shift, d1 = r.y - shift, d2 = r.z - shift, d3 = r.w - shift;
           sum += (d0 + d1) + (d2 + d3);
           sq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sq))));
@@ -210,31 +224,49 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) {
           tma_store_2d(&tmX, slab, c * 32, row0);
           bulk_commit_group();
-          // the slab of chunk c-1 is reusable once its store (the second newest group) has read it
-          if (c >= 1 && c - 1 + GLN_SLABS < Cfg::kChunks) {
+          // the slab of this warp's previous chunk is reusable once its store (the second newest group) has read it
+          if (i >= 1 && i - 1 + GLN_SLABS < Cfg::kMyChunks) {
             bulk_wait_group_read<1>();
-            const int sp = (c - 1) % GLN_SLABS;
+            const int sp = (i - 1) % GLN_SLABS;
             mbar_expect_tx(&my_xbar[sp], 4096);
-            tma_load_2d(my_slabs + sp * 4096, &tmX, &my_xbar[sp], (c - 1 + GLN_SLABS) * 32, row0);
+            tma_load_2d(my_slabs + sp * 4096, &tmX, &my_xbar[sp], (2 * (i - 1 + GLN_SLABS) + w) * 32, row0);
           }
         }
       }
-      const float mean_d = sum * (1.0f / D);
-      const float mean = shift + mean_d;
-      const float var = fmaxf(sq * (1.0f / D) - mean_d * mean_d, 0.0f);
+      // ---- combine the two partial statistics of the row (each over D/2 columns) ----
+      constexpr float kHalfN = 0.5f * D;
+      const float md = sum * (1.0f / kHalfN);
+      const float my_mean = shift + md;
+      const float my_m2 = fmaxf(sq - sum * md, 0.0f);
+      s_stat[(quarter * 2 + w) * 32 + lane] = make_float2(my_mean, my_m2);
+      tmem_st_wait();                                  // (also orders this warp's TMEM stores before the pair barrier)
+      tc_fence_before();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      tc_fence_after();
+      const float2 other = s_stat[(quarter * 2 + (w ^ 1)) * 32 + lane];
+      const float delta = other.x - my_mean;            // symmetric forms: both warps of the pair get identical bits
+      const float mean = 0.5f * (my_mean + other.x);
+      const float var = ((my_m2 + other.y) + delta * delta * (0.5f * kHalfN)) * (1.0f / D);
       const float rstd = 1.0f / sqrtf(var + p.eps);
-      tmem_st_wait();
-      if (lane == 0) bulk_wait_group_read<0>();        // every slab is free again
+      if (lane == 0) bulk_wait_group_read<0>();        // every slab of this warp is free again
       __syncwarp();
-      // ---- pass 2: normalise, bf16, 64 columns (128 B) per row per TMA store ----
+      // ---- pass 2: normalise, bf16, 64 columns (128 B) per row per TMA store; chunk c2 = 2 * i + w ----
+      int k2 = 0;
+      bool low_released = false;
 #pragma unroll 1
-      for (int c = 0; c < D / 64; ++c) {
-        uint8_t* slab = my_slabs + (c % GLN_SLABS) * 4096;
-        uint8_t* buf = slab + lane * 128;
-        if (c >= GLN_SLABS) {                           // (D = 384: 6 chunks, never taken)
+      for (int c = w; c < D / 64; c += 2, ++k2) {
+        if (c * 64 >= Cfg::kNH && !low_released) {      // this warp has read its last chunk of TMEM columns [0, D/2)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[0]);
+          low_released = true;
+        }
+        if (k2 >= GLN_SLABS) {                          // (never taken for D <= 384)
           if (lane == 0) bulk_wait_group_read<GLN_SLABS - 1>();
           __syncwarp();
         }
+        uint8_t* slab = my_slabs + (k2 % GLN_SLABS) * 4096;
+        uint8_t* buf = slab + lane * 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
@@ -264,7 +296,10 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_before();
       if (lane == 0) bulk_wait_group_read<0>();        // slabs free for the next tile's x loads
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[0]);
+      if (lane == 0) {
+        if (!low_released) mbar_arrive(&tempty_bar[0]);
+        mbar_arrive(&tempty_bar[1]);
+      }
       tphase ^= 1u;
     }
     if (lane == 0) bulk_wait_group<0>();

@@ -13,4 +13,3 @@ d = json.loads(sys.stdin.read())
 print(d['value'], 'img/s', d['ms_per_step'], 'ms/step | e2e', d['e2e']['value'], '| e2e_u8', d.get('e2e_u8', {}).get('value'), d['roofline']['by_category_ms'])"
 tail -1 gpurun_out/bench.err
 done
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vitstr.py -m gpu -q -x --timeout 600 2>&1 | tail -5

@@ -34,11 +34,14 @@ def _clear_decisions_identical(engine_logits, ref_logits, tau):
     return bool(same[clear].all()), int(clear.sum())
 
 
+@pytest.mark.parametrize("fuse", [None, 7], ids=["default", "fused_ln"])
 @pytest.mark.parametrize("path", CASES, ids=lambda p: os.path.basename(p)[:-3])
-def test_vs_reference_golden(path):
+def test_vs_reference_golden(path, fuse):
     from parseq_b200.weights import synth_images, state_dict_digest
     blob = torch.load(path, weights_only=False)
     cfg, sd, m = _model(blob["weight_seed"], **blob["overrides"])
+    if fuse is not None:          # small batches take the unfused pair by default: force the fused GEMM+LN kernels too
+        m.model.set_engine_option("fuse_ln", fuse)
     assert state_dict_digest(sd) == blob["sd_digest"]
     x = synth_images(cfg, blob["batch"], blob["image_seed"]).cuda()
     with torch.inference_mode():
