@@ -5,7 +5,7 @@ timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 12
 tail -25 gpurun_out/fuse_unit.log
 if grep -q "failed\|error" gpurun_out/fuse_unit.log; then echo "UNIT FAILED - stopping"; exit 0; fi
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
-for f in "" "--no-fuse-ln"; do
+for f in "--fuse-ln 3" "--fuse-ln 0"; do
 echo "== bench $f"
 timeout 300 python bench.py --no-cpu-baseline $f 2>gpurun_out/bench.err | tee gpurun_out/bench_last.json | python -c "
 import sys, json
