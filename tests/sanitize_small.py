@@ -13,6 +13,7 @@ for exp in ("parseq-tiny", "parseq"):
         m = create_model(exp, decode_ar=ar, refine_iters=ri)
         m.model.load_state_dict(sd)
         m.model.set_engine_option("use_graph", 0)
+        m.model.set_engine_option("fuse_ln", 7 if ar else 0)     # AR modes: fused residual-GEMM + LayerNorm kernels forced
         m = m.eval().to("cuda")
         x = synth_images(cfg, 3, 1).cuda()
         with torch.inference_mode():

@@ -35,6 +35,13 @@ def test_sass_is_blackwell_native():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in sass or "sm_100" in sass
+    # the fused residual-GEMM + LayerNorm kernel: UMMA + TMA load AND store + TMEM load AND store (the updated row is
+    # parked in TMEM between its two epilogue passes)
+    fn = [b for b in sass.split("Function : ")[1:] if "gemm_ln_fused_kernel" in b.split("\n", 1)[0]]
+    assert len(fn) == 2                       # D = 192 and D = 384
+    for body in fn:
+        for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
+            assert mnemonic in body, mnemonic
 
 
 def test_no_cpu_fallback():
