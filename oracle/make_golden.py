@@ -115,7 +115,7 @@ def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau):
                 margins.append(float(o.min_margin[k]))
         print(f"{name}: block {blk + 1}/{n_blocks} accepted so far {len(picks)}/{n_cand}", flush=True)
     blob = dict(name=name, experiment=exp, weight_seed=wseed, decode_ar=ar, refine_iters=ri, max_length=ml,
-                block=block, tau=tau, candidates=n_cand, picks=picks, ids=torch.stack(ids),
+                block=block, tau=tau, candidates=n_cand, acceptance_rate=len(picks) / max(1, n_cand), picks=picks, ids=torch.stack(ids),
                 logits=torch.stack(logits), margins=torch.tensor(margins), sd_digest=state_dict_digest(sd))
     torch.save(blob, os.path.join(OUT, name + ".pt"))
 
@@ -162,7 +162,9 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "filtered_ti":
         make_filtered("filtered_ti_ar1_len5", "parseq-tiny", 2, True, 1, 5, 4, 256, 0.012)
     elif len(sys.argv) > 1 and sys.argv[1] == "filtered":
-        make_filtered("filtered_s_ar1", "parseq", 0, True, 1, None, 16, 256, 0.02)
+        # 176 blocks of 256 candidates: ~0.25 % pass the margin filter at full length (a property of the near-flat random-init
+        # logits, not of the engine) -> >= 100 accepted sequences; ~25 CPU-minutes on 8 cores
+        make_filtered("filtered_s_ar1", "parseq", 0, True, 1, None, int(os.environ.get("FILTERED_BLOCKS", "176")), 256, 0.02)
         make_filtered("filtered_s_ar1_len5", "parseq", 0, True, 1, 5, 2, 256, 0.02)
         make_filtered("filtered_ti_ar1_len5", "parseq-tiny", 2, True, 1, 5, 4, 256, 0.012)
     else:
