@@ -46,23 +46,39 @@ CASES = [
 ]
 
 
-def make_sd(experiment, seed, eos_bias):
+# "sharp" cases (parseq_b200.weights._sharpen): q / k projections scaled 4x -> pre-softmax scores 16x -> peaked attention
+# rows, so that a wrong / missing q, mask or scale shows up well above the bf16 tolerance.  One per embed width and
+# decode mode.  Appended to CASES with a 10th field.
+SHARP_CASES = [
+    ("s_sharp_ar1_b2",   "parseq",             5, 0.0, 2, 20, True,  1, None, 4.0),
+    ("s_sharp_nar2_b2",  "parseq",             5, 0.0, 2, 21, False, 2, None, 4.0),
+    ("s_sharp_eos_ar1_b3", "parseq",           6, 0.6, 3, 22, True,  1, None, 4.0),
+    ("ti_sharp_ar1_b3",  "parseq-tiny",        7, 0.0, 3, 23, True,  1, None, 4.0),
+    ("ti_sharp_nar1_b2", "parseq-tiny",        7, 0.0, 2, 24, False, 1, None, 4.0),
+    ("b48_sharp_ar1_b2", "parseq-base-48x160", 8, 0.0, 2, 25, True,  1, None, 4.0),
+    ("p16_sharp_ar1_b2", "parseq-patch16-224", 9, 0.0, 2, 26, True,  1, None, 4.0),
+]
+
+
+def make_sd(experiment, seed, eos_bias, sharp=0.0):
     cfg = make_config(experiment)
-    sd = init_state_dict(cfg, seed)
+    sd = init_state_dict(cfg, seed, sharp=sharp)
     if eos_bias:
         sd["head.bias"] = sd["head.bias"].clone()
         sd["head.bias"][0] += eos_bias
     return cfg, sd
 
 
-def main():
+def main(cases=None):
     assert RL.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
     cache = {}
-    for name, exp, wseed, eos_bias, B, iseed, ar, ri, ml in CASES:
-        key = (exp, wseed, eos_bias)
+    for case in (cases if cases is not None else CASES + SHARP_CASES):
+        name, exp, wseed, eos_bias, B, iseed, ar, ri, ml = case[:9]
+        sharp = case[9] if len(case) > 9 else 0.0
+        key = (exp, wseed, eos_bias, sharp)
         if key not in cache:
-            cfg, sd = make_sd(exp, wseed, eos_bias)
+            cfg, sd = make_sd(exp, wseed, eos_bias, sharp)
             ref, tok = RL.build_reference_model(cfg, sd)
             cache[key] = (cfg, sd, ref, tok, ParseqOracle(cfg, sd, "fp64"))
         cfg, sd, ref, tok, o64 = cache[key]
@@ -74,9 +90,11 @@ def main():
         o = o64.forward(x, ml, ar, ri)
         assert o.logits.shape == logits.shape, (name, o.logits.shape, logits.shape)
         err = (o.logits.float() - logits).abs().max().item()
-        assert err < 1e-5, (name, err)          # pins the oracle (and its id trajectory) to the reference
+        # pins the oracle (and its id trajectory) to the reference; the sharp cases amplify the reference's own fp32
+        # round-off (fp64 oracle vs fp32 reference: 1.7e-5 at D = 768)
+        assert err < (5e-5 if sharp else 1e-5), (name, err)
         blob = dict(
-            name=name, experiment=exp, weight_seed=wseed, eos_bias=eos_bias, batch=B, image_seed=iseed,
+            name=name, experiment=exp, weight_seed=wseed, eos_bias=eos_bias, sharp=sharp, batch=B, image_seed=iseed,
             decode_ar=ar, refine_iters=ri, max_length=ml, sd_digest=state_dict_digest(sd),
             logits=logits.contiguous(), memory0=memory[0].contiguous(),
             min_margin_fp64=o.min_margin.float(), steps=o.steps,
@@ -91,7 +109,7 @@ def main():
               f"min margin {o.min_margin.min().item():.2e}")
 
 
-def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau):
+def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau, first_block=0):
     """Margin-filtered free-running set: candidates whose smallest top1-top2 margin over
     every argmax decision of the fp32 reference run exceeds `tau`; on these, decoded ids must be bit-identical
     between the bf16 engine and the fp32 reference."""
@@ -100,7 +118,7 @@ def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau):
     ref.decode_ar, ref.refine_iters = ar, ri
     o32 = ParseqOracle(cfg, sd, "fp32")
     picks, ids, logits, margins, n_cand = [], [], [], [], 0
-    for blk in range(n_blocks):
+    for blk in range(first_block, first_block + n_blocks):
         seed = 90_000 + blk
         x = synth_images(cfg, block, seed)
         o = o32.forward(x, ml, ar, ri)
@@ -113,7 +131,7 @@ def make_filtered(name, exp, wseed, ar, ri, ml, n_blocks, block, tau):
             for j, k in enumerate(keep):
                 picks.append((seed, k)); ids.append(lr[j].argmax(-1).int()); logits.append(lr[j].clone())
                 margins.append(float(o.min_margin[k]))
-        print(f"{name}: block {blk + 1}/{n_blocks} accepted so far {len(picks)}/{n_cand}", flush=True)
+        print(f"{name}: block {blk + 1}/{first_block + n_blocks} accepted so far {len(picks)}/{n_cand}", flush=True)
     blob = dict(name=name, experiment=exp, weight_seed=wseed, decode_ar=ar, refine_iters=ri, max_length=ml,
                 block=block, tau=tau, candidates=n_cand, acceptance_rate=len(picks) / max(1, n_cand), picks=picks, ids=torch.stack(ids),
                 logits=torch.stack(logits), margins=torch.tensor(margins), sd_digest=state_dict_digest(sd))
@@ -159,8 +177,28 @@ def make_vitstr():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "vitstr":
         make_vitstr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sharp":
+        main(SHARP_CASES)
     elif len(sys.argv) > 1 and sys.argv[1] == "filtered_ti":
         make_filtered("filtered_ti_ar1_len5", "parseq-tiny", 2, True, 1, 5, 4, 256, 0.012)
+    elif len(sys.argv) > 1 and sys.argv[1] == "filtered_more":
+        # extra candidate blocks [first, first + n) for the full-length set, written to <name>_part.pt; merge with
+        # `python -m oracle.make_golden filtered_merge`
+        first, n = int(sys.argv[2]), int(sys.argv[3])
+        make_filtered("filtered_s_ar1_part", "parseq", 0, True, 1, None, n, 256, 0.02, first_block=first)
+    elif len(sys.argv) > 1 and sys.argv[1] == "filtered_merge":
+        a = torch.load(os.path.join(OUT, "filtered_s_ar1.pt"), weights_only=False)
+        b = torch.load(os.path.join(OUT, "filtered_s_ar1_part.pt"), weights_only=False)
+        assert a["sd_digest"] == b["sd_digest"] and a["tau"] == b["tau"] and a["block"] == b["block"]
+        assert not (set(a["picks"]) & set(b["picks"]))
+        a["picks"] = a["picks"] + b["picks"]
+        for k in ("ids", "logits", "margins"):
+            a[k] = torch.cat([a[k], b[k]])
+        a["candidates"] += b["candidates"]
+        a["acceptance_rate"] = len(a["picks"]) / a["candidates"]
+        torch.save(a, os.path.join(OUT, "filtered_s_ar1.pt"))
+        os.remove(os.path.join(OUT, "filtered_s_ar1_part.pt"))
+        print("merged:", len(a["picks"]), "picks of", a["candidates"], "candidates")
     elif len(sys.argv) > 1 and sys.argv[1] == "filtered":
         # 176 blocks of 256 candidates: ~0.25 % pass the margin filter at full length (a property of the near-flat random-init
         # logits, not of the engine) -> >= 100 accepted sequences; ~25 CPU-minutes on 8 cores

@@ -283,6 +283,7 @@ __device__ void dec_tile(const DecArParams& p, unsigned char* smem, const __nv_b
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int c = n0 + (nh * NT + nt) * 8 + 2 * t;
+    if (c >= N) continue;                            // ragged last column tile (D = 192 with 128-wide tiles); N is even
     const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c));
     float v00 = acc[nt][0] + bb.x, v01 = acc[nt][1] + bb.y, v10 = acc[nt][2] + bb.x, v11 = acc[nt][3] + bb.y;
     if (EPI == DE_POSQ) {
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
     DEC_PROF(4);
     // ---------------- P3: qc = scale * q_proj(LN1(y)) ----------------
     {
-      const int mt16 = (p.B + 15) / 16, ntq = D / 128;
+      const int mt16 = (p.B + 15) / 16, ntq = (D + 127) / 128;   // D = 192: second tile is half empty
       for (int tile = blockIdx.x; tile < mt16 * ntq; tile += gridDim.x)
         dec_tile<D, 2, true, DE_SCALE, 1>(p, dec_smem, nullptr, 0, p.y, p.g1, p.be1, p.Wq_c, D, D, p.bq_c, (tile / ntq) * 16,
                                           (tile % ntq) * 128, step);

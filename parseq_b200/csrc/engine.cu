@@ -84,12 +84,31 @@ uint16_t f32_to_bf16_rne(float f) {
   return static_cast<uint16_t>(u >> 16);
 }
 
-int g_sm_count = 0;
-bool g_use_pdl = true;          // programmatic dependent launch on every kernel of the forward chain
+// Launch options.  Every engine handle owns one (parseq_set_option(handle, ...)); `g_default_opts` serves only the
+// bare kernel exports (parseq_gemm_bf16 & co., unit tests) and parseq_set_option(NULL, ...).
+struct LaunchOpts {
+  int sm_count = 0;
+  bool use_pdl = true;          // programmatic dependent launch on every kernel of the forward chain
+  int block_n = 0;              // 0 = auto
+  int cta_group = 0;            // 0 = auto, 1 / 2 = forced (tests)
+  bool no_tma_epilogue = false; // tests: force the direct-store epilogue
+  int gemm_stages = 0;          // experiments: cap the operand ring depth (0 = full)
+  int attn_impl = 1;            // 1: tcgen05 kernel (attn_tc.cuh), 0: mma.sync kernel (kernels.cuh)
+};
+LaunchOpts g_default_opts;
+
+int ensure_sm_count(LaunchOpts& o) {
+  if (o.sm_count == 0) {
+    int dev = 0;
+    PQ_CUDA(cudaGetDevice(&dev));
+    PQ_CUDA(cudaDeviceGetAttribute(&o.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return PARSEQ_OK;
+}
 
 // cudaLaunchKernelEx wrapper: optional PDL attribute (the kernels call griddepcontrol.{launch_dependents,wait}).
 template <typename... KArgs, typename... Args>
-int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+int launch_k(const LaunchOpts& lo, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -99,19 +118,14 @@ int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = lo.use_pdl ? 1 : 0;
   PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
   return PARSEQ_OK;
 }
 
-int g_block_n_override = 0;
-int g_cta_group_override = 0;   // 0 = auto, 1 / 2 = forced (tests)
-bool g_no_tma_epilogue = false; // tests: force the direct-store epilogue
-int g_gemm_stages = 0;          // experiments: cap the operand ring depth (0 = full)
-
 template <int BN, int CG>
-int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const pq::GemmParams& p, int tiles,
-                    cudaStream_t st) {
+int launch_gemm_cfg(const LaunchOpts& lo, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                    const pq::GemmParams& p, int tiles, cudaStream_t st) {
   auto kern = pq::gemm_bf16_tcgen05_kernel<BN, CG>;
   using Cfg = pq::GemmCfg<BN, CG>;
   static bool attr_set = false;
@@ -119,7 +133,7 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
     PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int max_groups = g_sm_count / CG;
+  const int max_groups = lo.sm_count / CG;
   const int groups = tiles < max_groups ? tiles : max_groups;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
@@ -134,7 +148,7 @@ int launch_gemm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (g_use_pdl && CG == 1) ? 2 : 1;
+  cfg.numAttrs = (lo.use_pdl && CG == 1) ? 2 : 1;
   PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return PARSEQ_OK;
 }
@@ -150,18 +164,18 @@ size_t head_smem_bytes(int C, int D) {
   return ((static_cast<size_t>(C) * (D / 2 + 1) * 4 + 15) / 16) * 16 + static_cast<size_t>(pq::HEAD_ROWS) * D * 4 +
          4 * pq::HEAD_ROWS * 128 * 4 + pq::HEAD_ROWS * 128 * 4;
 }
-int ln_head_argmax_launch(const float* y, const float* g, const float* b, float eps, const __nv_bfloat16* Wh, const float* bh,
+int ln_head_argmax_launch(const LaunchOpts& lo, const float* y, const float* g, const float* b, float eps, const __nv_bfloat16* Wh, const float* bh,
                           int M, int C, int D, float* logits, long long logits_ld, int* ids, int ids_ld, int nq, int dst_off,
                           const int* forced, int forced_ld, cudaStream_t st) {
   if (C > 128) return fail(PARSEQ_ERR_UNSUPPORTED, "head kernel covers at most 128 classes");
   const dim3 grid((M + pq::HEAD_ROWS - 1) / pq::HEAD_ROWS), block(384);
   const size_t sm = head_smem_bytes(C, D);
   switch (D) {
-    case 192: return launch_k(pq::dec_ln_head_argmax_kernel<192>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
+    case 192: return launch_k(lo, pq::dec_ln_head_argmax_kernel<192>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
                               logits_ld, ids, ids_ld, nq, dst_off, forced, forced_ld);
-    case 384: return launch_k(pq::dec_ln_head_argmax_kernel<384>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
+    case 384: return launch_k(lo, pq::dec_ln_head_argmax_kernel<384>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
                               logits_ld, ids, ids_ld, nq, dst_off, forced, forced_ld);
-    case 768: return launch_k(pq::dec_ln_head_argmax_kernel<768>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
+    case 768: return launch_k(lo, pq::dec_ln_head_argmax_kernel<768>, grid, block, sm, st, y, g, b, eps, Wh, bh, M, C, logits,
                               logits_ld, ids, ids_ld, nq, dst_off, forced, forced_ld);
     default: return fail(PARSEQ_ERR_UNSUPPORTED, "head kernel: embed_dim must be 192, 384 or 768");
   }
@@ -190,27 +204,22 @@ int init_kernel_attributes() {
   return PARSEQ_OK;
 }
 
-int gemm_launch(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
-                int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
+int gemm_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N,
+                int K, int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
                 cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm: empty problem");
-  if (g_sm_count == 0) {
-    int dev = 0;
-    PQ_CUDA(cudaGetDevice(&dev));
-    PQ_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  PQ_TRY(ensure_sm_count(lo));
   // Tile choice from tests/bench_gemm.py on B200 (profiles/r1_gemm_microbench*.txt): single-CTA 128 x 256 tiles win
   // for the wide projections (QKV 1152 -> 4.5 tiles, fc1 1536), 128 x 192 for N = 384 / 768 (no padded columns),
   // 128 x 128 for the small decoder GEMMs; the CTA-pair variant (cta_group::2) is correct but slower with this pipeline depth, so it is opt-in.
   int CG = 1;
-  if (g_cta_group_override) CG = g_cta_group_override;
+  if (lo.cta_group) CG = lo.cta_group;
   int BN;
   if (CG == 2) BN = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : 128;
   else BN = (N <= 64) ? 64 : (M < 1024) ? 128 : (N >= 1024) ? 256 : (N % 192 == 0) ? 192 : 128;
-  if (g_block_n_override) {
-    BN = g_block_n_override;
+  if (lo.block_n) {
+    BN = lo.block_n;
     if (CG == 2 && BN == 64) BN = 128;
-
   }
   CUtensorMap ta, tb, tc;
   PQ_TRY(make_tmap(&ta, A, 2, M, K, lda, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
@@ -225,7 +234,7 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
   p.vec_ok = vec ? 1 : 0;
   // asynchronous TMA epilogue whenever the output is TMA-addressable; residual only as in-place accumulate
   p.tma_out = 0;
-  const bool out_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((ldo * esz) % 16 == 0) && !g_no_tma_epilogue;
+  const bool out_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((ldo * esz) % 16 == 0) && !lo.no_tma_epilogue;
   if (out_ok) {
     if (mode != pq::EPI_F32) p.tma_out = 3;
     else if (resid == nullptr) p.tma_out = 1;
@@ -235,25 +244,25 @@ int gemm_launch(const void* A, long long lda, const void* W, long long ldw, cons
   else if (p.tma_out != 0) PQ_TRY(make_tmap(&tc, out, 4, M, N, ldo, 32, 32));
   else tc = ta;
   const int tile_m = pq::GEMM_BLOCK_M * CG;
-  p.max_stages = g_gemm_stages;
+  p.max_stages = lo.gemm_stages;
   p.num_m_tiles = (M + tile_m - 1) / tile_m;
   p.num_n_tiles = (N + BN - 1) / BN;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (CG == 2) {
-    if (BN == 256) return launch_gemm_cfg<256, 2>(ta, tb, tc, p, tiles, st);
-    if (BN == 192) return launch_gemm_cfg<192, 2>(ta, tb, tc, p, tiles, st);
-    return launch_gemm_cfg<128, 2>(ta, tb, tc, p, tiles, st);
+    if (BN == 256) return launch_gemm_cfg<256, 2>(lo, ta, tb, tc, p, tiles, st);
+    if (BN == 192) return launch_gemm_cfg<192, 2>(lo, ta, tb, tc, p, tiles, st);
+    return launch_gemm_cfg<128, 2>(lo, ta, tb, tc, p, tiles, st);
   }
-  if (BN == 256) return launch_gemm_cfg<256, 1>(ta, tb, tc, p, tiles, st);
-  if (BN == 192) return launch_gemm_cfg<192, 1>(ta, tb, tc, p, tiles, st);
-  if (BN == 64) return launch_gemm_cfg<64, 1>(ta, tb, tc, p, tiles, st);
-  return launch_gemm_cfg<128, 1>(ta, tb, tc, p, tiles, st);
+  if (BN == 256) return launch_gemm_cfg<256, 1>(lo, ta, tb, tc, p, tiles, st);
+  if (BN == 192) return launch_gemm_cfg<192, 1>(lo, ta, tb, tc, p, tiles, st);
+  if (BN == 64) return launch_gemm_cfg<64, 1>(lo, ta, tb, tc, p, tiles, st);
+  return launch_gemm_cfg<128, 1>(lo, ta, tb, tc, p, tiles, st);
 }
 
 // x[M, D] += A[M, K] * W[D, K]^T + bias (fp32, in place); xn[M, D] = bf16(LayerNorm(x; gamma, beta, eps))   (gemm_ln.cuh)
 bool gemm_ln_supported(int D) { return D == 192 || D == 384; }
 template <int D>
-int launch_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int K, float* x,
+int launch_gemm_ln(const LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int K, float* x,
                    const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
   using Cfg = pq::GemmLnCfg<D>;
   auto kern = pq::gemm_ln_fused_kernel<D>;
@@ -270,45 +279,39 @@ int launch_gemm_ln(const void* A, long long lda, const void* W, long long ldw, c
   pq::GemmLnParams p;
   p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
   p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
-  const int grid = p.num_m_tiles < g_sm_count ? p.num_m_tiles : g_sm_count;
-  return launch_k(kern, dim3(grid), dim3(pq::GLN_THREADS), Cfg::kSmemBytes, st, ta, tb, tx, tn, p);
+  const int grid = p.num_m_tiles < lo.sm_count ? p.num_m_tiles : lo.sm_count;
+  return launch_k(lo, kern, dim3(grid), dim3(pq::GLN_THREADS), Cfg::kSmemBytes, st, ta, tb, tx, tn, p);
 }
-int gemm_ln_launch(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int D, int K,
-                   float* x, const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
+int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int D,
+                   int K, float* x, const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
   if (M <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm_ln: empty problem");
-  if (g_sm_count == 0) {
-    int dev = 0;
-    PQ_CUDA(cudaGetDevice(&dev));
-    PQ_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  PQ_TRY(ensure_sm_count(lo));
   PQ_TRY(load_driver_api());
-  if (D == 384) return launch_gemm_ln<384>(A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
-  if (D == 192) return launch_gemm_ln<192>(A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  if (D == 384) return launch_gemm_ln<384>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  if (D == 192) return launch_gemm_ln<192>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
   return fail(PARSEQ_ERR_UNSUPPORTED, "gemm_ln: embed_dim must be 192 or 384 (full rows in 512 TMEM columns)");
 }
 
-int layernorm_launch(const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
+int layernorm_launch(const LaunchOpts& lo, const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
                      cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   const int rows_per_block = 8;
   const int grid = (M + rows_per_block - 1) / rows_per_block;
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
   switch (D) {
-    case 192: return launch_k(pq::layernorm_kernel<192>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
-    case 384: return launch_k(pq::layernorm_kernel<384>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
-    case 768: return launch_k(pq::layernorm_kernel<768>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
+    case 192: return launch_k(lo, pq::layernorm_kernel<192>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
+    case 384: return launch_k(lo, pq::layernorm_kernel<384>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
+    case 768: return launch_k(lo, pq::layernorm_kernel<768>, dim3(grid), dim3(256), 0, st, x, g, b, eps, M, yb, y32, add, add_mod, xw);
     default: return fail(PARSEQ_ERR_UNSUPPORTED, "layernorm: embed_dim must be 192, 384 or 768");
   }
 }
 
-int g_attn_impl = 1;   // 1: tcgen05 kernel (attn_tc.cuh), 0: mma.sync kernel (kernels.cuh)
-
-int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
+int enc_attention_launch(const LaunchOpts& lo, const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
   if (D != heads * pq::ATT_DH) return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernels cover head_dim=64");
   if (T != pq::ATT_T) {   // general token count: masked two-pass mma.sync kernel
-    return launch_k(pq::enc_attention_any_kernel, dim3(B * heads, (T + pq::ATT_T - 1) / pq::ATT_T), dim3(256), 0, st,
+    return launch_k(lo, pq::enc_attention_any_kernel, dim3(B * heads, (T + pq::ATT_T - 1) / pq::ATT_T), dim3(256), 0, st,
                     reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), T, D, heads);
   }
-  if (g_attn_impl == 1) {
+  if (lo.attn_impl == 1) {
     static bool attr_set = false;
     if (!attr_set) {
       PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::ATC_SMEM_BYTES));
@@ -317,9 +320,9 @@ int enc_attention_launch(const void* qkv, int B, int T, int D, int heads, void* 
     CUtensorMap tq, to;
     PQ_TRY(make_tmap(&tq, qkv, 2, static_cast<long long>(B) * T, 3ll * D, 3ll * D, 64, 128));
     PQ_TRY(make_tmap(&to, out, 2, static_cast<long long>(B) * T, D, D, 64, 32));
-    return launch_k(pq::enc_attention_tc_kernel, dim3(B * heads), dim3(pq::ATC_THREADS), pq::ATC_SMEM_BYTES, st, tq, to, D, heads);
+    return launch_k(lo, pq::enc_attention_tc_kernel, dim3(B * heads), dim3(pq::ATC_THREADS), pq::ATC_SMEM_BYTES, st, tq, to, D, heads);
   }
-  return launch_k(pq::enc_attention_kernel, dim3(B * heads), dim3(256), 0, st,
+  return launch_k(lo, pq::enc_attention_kernel, dim3(B * heads), dim3(256), 0, st,
                   reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), D, heads);
 }
 
@@ -344,6 +347,8 @@ struct parseq_engine {
   std::vector<Slot> slots;
   std::map<std::string, int> index;
   bool finalized = false;
+  bool broken = false;                               // workspace could not be (re)allocated: every forward fails
+  LaunchOpts lo;                                     // per-handle launch options
   long long launches = 0;
   // optional per-category device timing (bench.py roofline pass; off on the throughput pass)
   bool timing = false;
@@ -511,19 +516,19 @@ int gemm(parseq_engine* e, const void* A, long long lda, const void* W, long lon
          int K, int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
          cudaStream_t st) {
   TimedScope ts(e, st, e->cur_cat == CAT_DEC_GEMM ? CAT_DEC_GEMM : CAT_ENC_GEMM, 2.0 * M * N * K);
-  return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st);
+  return gemm_launch(e->lo, A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st);
 }
 // x += A W^T + b;  y = bf16(LayerNorm(x; <ln_prefix>))  in one kernel
 int gemm_ln(parseq_engine* e, const void* A, long long lda, const std::string& lin, int M, int K, float* x,
             const std::string& ln_prefix, float eps, void* y, cudaStream_t st) {
   TimedScope ts(e, st, CAT_ENC_GEMM_LN, 2.0 * M * e->D * K);
-  return gemm_ln_launch(A, lda, e->w(lin + ".weight"), K, e->wf(lin + ".bias"), M, e->D, K, x, e->wf(ln_prefix + ".weight"),
+  return gemm_ln_launch(e->lo, A, lda, e->w(lin + ".weight"), K, e->wf(lin + ".bias"), M, e->D, K, x, e->wf(ln_prefix + ".weight"),
                         e->wf(ln_prefix + ".bias"), eps, y, st);
 }
 int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float eps, int M, void* y, float* y32,
               cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   TimedScope ts(e, st, CAT_LN, 0.0);
-  return layernorm_launch(x, e->wf(prefix + ".weight"), e->wf(prefix + ".bias"), eps, M, e->D, y, y32, st, add, add_mod, xw);
+  return layernorm_launch(e->lo, x, e->wf(prefix + ".weight"), e->wf(prefix + ".bias"), eps, M, e->D, y, y32, st, add, add_mod, xw);
 }
 
 // ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
@@ -536,12 +541,12 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
     if (u8) {
       const long long total = static_cast<long long>(B) * e->gh * e->gw * e->cfg.patch_h;
       const int grid = static_cast<int>((total + 255) / 256);
-      PQ_TRY(launch_k(pq::im2col_patch_u8_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(images_any), e->a_pe,
+      PQ_TRY(launch_k(e->lo, pq::im2col_patch_u8_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(images_any), e->a_pe,
                       B, e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
     } else {
       const long long total = static_cast<long long>(B) * e->gh * e->gw * 3 * e->cfg.patch_h;
       const int grid = static_cast<int>((total + 255) / 256);
-      PQ_TRY(launch_k(pq::im2col_patch_kernel, dim3(grid), dim3(256), 0, st, static_cast<const float*>(images_any), e->a_pe, B,
+      PQ_TRY(launch_k(e->lo, pq::im2col_patch_kernel, dim3(grid), dim3(256), 0, st, static_cast<const float*>(images_any), e->a_pe, B,
                       e->cfg.img_h, e->cfg.img_w, e->cfg.patch_h, e->cfg.patch_w, e->gh, e->gw));
     }
   }
@@ -559,7 +564,7 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
     TimedScope ts(e, st, CAT_MISC, 0.0);
     const long long total = 1ll * M * (D / 4);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148ll * 16));
-    PQ_TRY(launch_k(pq::cls_assemble_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(tmp),
+    PQ_TRY(launch_k(e->lo, pq::cls_assemble_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(tmp),
                     reinterpret_cast<const float4*>(e->wf("encoder.cls_token")),
                     reinterpret_cast<const float4*>(e->wf("encoder.pos_embed")), reinterpret_cast<float4*>(e->x), B, e->Tp,
                     D / 4));
@@ -570,7 +575,7 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
   // The fused kernel owns whole 128-row tiles (one CTA per tile, both column halves in sequence): it pays off once
   // the tiles fill the machine about twice; below that the N-split GEMM + LayerNorm pair has the lower latency
   // (bs=1: 1.67 ms vs 1.93 ms p50).  "fuse_ln" bit 2 forces it for any M (tests).
-  const bool big = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M >= 2 * g_sm_count || (e->fuse_ln & 4);
+  const bool big = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M >= 2 * e->lo.sm_count || (e->fuse_ln & 4);
   const bool fuse_proj = (e->fuse_ln & 1) && gemm_ln_supported(D) && big;
   const bool fuse_fc2 = (e->fuse_ln & 2) && gemm_ln_supported(D) && big;
   bool final_done = false;
@@ -582,7 +587,7 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
                 1.0f, nullptr, 0, 0, e->qkv, 3 * D, st));
     {
       TimedScope ts(e, st, CAT_ENC_ATTN, 4.0 * B * T * T * D);
-      PQ_TRY(enc_attention_launch(e->qkv, B, T, D, e->cfg.enc_num_heads, e->att, st));
+      PQ_TRY(enc_attention_launch(e->lo, e->qkv, B, T, D, e->cfg.enc_num_heads, e->att, st));
     }
     if (fuse_proj) {
       PQ_TRY(gemm_ln(e, e->att, D, p + "attn.proj", M, D, e->x, p + "norm2", 1e-6f, e->xn, st));
@@ -620,7 +625,7 @@ int vitstr_tail(parseq_engine* e, int B, int L, float* logits, int* ids_out, cud
     TimedScope ts(e, st, CAT_MISC, 0.0);
     const long long total = 1ll * M * (D / 4);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148ll * 16));
-    PQ_TRY(launch_k(pq::gather_token_rows_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(e->x),
+    PQ_TRY(launch_k(e->lo, pq::gather_token_rows_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(e->x),
                     reinterpret_cast<float4*>(e->vt_rows), B, e->T, 1, L, D / 4));
   }
   PQ_TRY(layernorm(e, e->vt_rows, "encoder.norm", 1e-6f, M, e->xn, nullptr, st));
@@ -645,7 +650,7 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
     const int qsplit = (nq >= 8) ? 4 : 1;
-    PQ_TRY(launch_k(pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D < 384 ? D : 384), 0, st, static_cast<const float*>(e->qs),
+    PQ_TRY(launch_k(e->lo, pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D < 384 ? D : 384), 0, st, static_cast<const float*>(e->qs),
                     static_cast<const __nv_bfloat16*>(e->kvtab), ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa,
                     qsplit));
   }
@@ -659,10 +664,10 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
     if (e->T <= 128)
-      PQ_TRY(launch_k(pq::dec_cross_attn3_kernel<4>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
+      PQ_TRY(launch_k(e->lo, pq::dec_cross_attn3_kernel<4>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
                       static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
     else
-      PQ_TRY(launch_k(pq::dec_cross_attn3_kernel<8>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
+      PQ_TRY(launch_k(e->lo, pq::dec_cross_attn3_kernel<8>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
                       static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
   }
   PQ_TRY(gemm(e, sg.ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
@@ -680,7 +685,7 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
                 logits_out, logits_ld, st));
   } else {
     TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * M * e->C * D);
-    PQ_TRY(ln_head_argmax_launch(sg.y, e->wf("decoder.norm.weight"), e->wf("decoder.norm.bias"), 1e-5f, e->wb("head.weight"),
+    PQ_TRY(ln_head_argmax_launch(e->lo, sg.y, e->wf("decoder.norm.weight"), e->wf("decoder.norm.bias"), 1e-5f, e->wb("head.weight"),
                                  e->wf("head.bias"), M, e->C, D, logits_out, logits_ld, ids_dst, 32, nq, dst_off, forced,
                                  forced_ld, st));
   }
@@ -692,7 +697,7 @@ int argmax_rows(parseq_engine* e, const float* logits, int L, int B, int nrows, 
   const int warps = B * nrows;
   if (warps <= 0) return PARSEQ_OK;
   TimedScope ts(e, st, CAT_MISC, 0.0);
-  return launch_k(pq::argmax_rows_kernel, dim3((warps + 7) / 8), dim3(256), 0, st, logits, L, e->C, B, nrows, src0, ids, ids_ld,
+  return launch_k(e->lo, pq::argmax_rows_kernel, dim3((warps + 7) / 8), dim3(256), 0, st, logits, L, e->C, B, nrows, src0, ids, ids_ld,
                   dst0, forced, forced_ld);
 }
 
@@ -707,7 +712,7 @@ int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16
   if (a->decode_ar && ar_done) {
     // the AR loop of the whole super-chunk already ran in the persistent kernel (ar_decode)
   } else if (a->decode_ar) {
-    PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ar, B, 32, bos, pad));
+    PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ar, B, 32, bos, pad));
     e->launches++;
     const int* forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
     for (int i = 0; i < L; ++i) {
@@ -716,16 +721,16 @@ int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16
                          (i + 1 < L) ? sg.ids_ar : nullptr, i + 1, forced, L, st));
     }
     if (testing && steps != nullptr) {
-      PQ_TRY(launch_k(pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(sg.ids_ar), 32, B, L, 0, steps));
+      PQ_TRY(launch_k(e->lo, pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(sg.ids_ar), 32, B, L, 0, steps));
       e->launches++;
     }
   } else {
-    PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
+    PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
     e->launches++;
     PQ_TRY(decode_pass(e, sg, ckv, B, L, 0, 1, 0, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
   }
   for (int it = 0; it < a->refine_iters; ++it) {
-    PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
+    PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
     e->launches++;
     const int* forced = a->forced_refine
                             ? a->forced_refine + (static_cast<long long>(it) * a->batch + b0) * L
@@ -743,7 +748,7 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
   const int D = e->D;
   const std::string Ly = "decoder.layers.0.";
   const bool testing = a->max_length < 0;
-  PQ_TRY(launch_k(pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, e->ar_ids, B, 32, e->V - 2, e->V - 1));
+  PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, e->ar_ids, B, 32, e->V - 2, e->V - 1));
   e->launches++;
   PQ_CUDA(cudaMemsetAsync(e->ar_bar, 0, 64, st));
   pq::DecArParams p;
@@ -770,25 +775,25 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
     // per image and step: 3 D^2 (self out, cross q, cross out) + 2 D Md (MLP) + C D (head) + attention dots
     const double macs = static_cast<double>(B) * L * (3.0 * D * D + 2.0 * D * e->Md + 1.0 * e->C * D + 2.0 * e->T * D);
     TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * macs);
-    const dim3 grid(static_cast<unsigned>(g_sm_count)), block(pq::DEC_THREADS);
+    const dim3 grid(static_cast<unsigned>(e->lo.sm_count)), block(pq::DEC_THREADS);
     switch (D) {
       case 192:
-        if (e->T <= 128) PQ_TRY(launch_k(pq::dec_ar_kernel<192, 1>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p));
-        else PQ_TRY(launch_k(pq::dec_ar_kernel<192, 2>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p));
+        if (e->T <= 128) PQ_TRY(launch_k(e->lo, pq::dec_ar_kernel<192, 1>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p));
+        else PQ_TRY(launch_k(e->lo, pq::dec_ar_kernel<192, 2>, grid, block, pq::dec_ar_smem_bytes<192>(), st, p));
         break;
       case 384:
-        if (e->T <= 128) PQ_TRY(launch_k(pq::dec_ar_kernel<384, 1>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p));
-        else PQ_TRY(launch_k(pq::dec_ar_kernel<384, 2>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p));
+        if (e->T <= 128) PQ_TRY(launch_k(e->lo, pq::dec_ar_kernel<384, 1>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p));
+        else PQ_TRY(launch_k(e->lo, pq::dec_ar_kernel<384, 2>, grid, block, pq::dec_ar_smem_bytes<384>(), st, p));
         break;
       case 768:
-        if (e->T <= 128) PQ_TRY(launch_k(pq::dec_ar_kernel<768, 1>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p));
-        else PQ_TRY(launch_k(pq::dec_ar_kernel<768, 2>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p));
+        if (e->T <= 128) PQ_TRY(launch_k(e->lo, pq::dec_ar_kernel<768, 1>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p));
+        else PQ_TRY(launch_k(e->lo, pq::dec_ar_kernel<768, 2>, grid, block, pq::dec_ar_smem_bytes<768>(), st, p));
         break;
       default: return fail(PARSEQ_ERR_UNSUPPORTED, "dec_ar: embed_dim must be 192, 384 or 768");
     }
   }
   if (testing && steps != nullptr) {
-    PQ_TRY(launch_k(pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(e->ar_ids), 32, B, L, 0, steps));
+    PQ_TRY(launch_k(e->lo, pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(e->ar_ids), 32, B, L, 0, steps));
     e->launches++;
   }
   return PARSEQ_OK;
@@ -897,7 +902,7 @@ int forward_impl(parseq_engine* e, const parseq_forward_args* a, const void* ima
   // user stream -> main
   PQ_CUDA(cudaEventRecord(e->ev_in, user));
   PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
-  PQ_TRY(launch_k(pq::set_int_kernel, dim3(1), dim3(32), 0, e->main, e->out_steps,
+  PQ_TRY(launch_k(e->lo, pq::set_int_kernel, dim3(1), dim3(32), 0, e->main, e->out_steps,
                   (testing && a->decode_ar && e->arch == 0) ? 0 : L));
   e->launches++;
   for (int b0 = 0; b0 < a->batch; b0 += e->max_batch) {
@@ -945,7 +950,7 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   if (prop.major != 10)
     return fail(PARSEQ_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                           ", the kernels are sm_100a (B200) only");
-  g_sm_count = prop.multiProcessorCount;
+  const int sm_count = prop.multiProcessorCount;
   PQ_TRY(init_kernel_attributes());
   PQ_TRY(load_driver_api());
   if (cfg->arch != 0 && cfg->arch != 1) return fail(PARSEQ_ERR_INVALID_ARG, "arch: 0 (PARSeq) or 1 (ViTSTR)");
@@ -957,8 +962,19 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   if (D != cfg->enc_num_heads * 64) return fail(PARSEQ_ERR_UNSUPPORTED, "encoder head_dim must be 64");
   if (!vitstr && D != cfg->dec_num_heads * 32) return fail(PARSEQ_ERR_UNSUPPORTED, "decoder head_dim must be 32");
   if (cfg->max_label_length + 1 > 32) return fail(PARSEQ_ERR_UNSUPPORTED, "max_label_length must be <= 31");
+  if (cfg->max_label_length < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative max_label_length");
+  // the head tiles of the decoder kernels hold one row of logits in 128 columns (charset_train of <= 126 characters;
+  // the reference's largest, 94_full, has 94)
+  if (cfg->num_tokens < 4 || cfg->num_tokens - 2 > 128)
+    return fail(PARSEQ_ERR_UNSUPPORTED, "num_tokens must be in [4, 130] (at most 128 head classes)");
+  if (cfg->enc_mlp_ratio < 1 || cfg->enc_depth < 1) return fail(PARSEQ_ERR_INVALID_ARG, "enc_mlp_ratio / enc_depth");
+  // decoder MLP: 128-wide linear1 tiles and a 3-way split-K of linear2 in 64-element k-blocks
+  if (!vitstr && (cfg->dec_mlp_ratio < 1 || (D * cfg->dec_mlp_ratio) % 384 != 0))
+    return fail(PARSEQ_ERR_UNSUPPORTED, "embed_dim * dec_mlp_ratio must be a multiple of 384");
   auto* e = new parseq_engine();
   e->cfg = *cfg;
+  e->lo = g_default_opts;         // process defaults (parseq_set_option(NULL, ...)) seed a new handle
+  e->lo.sm_count = sm_count;
   if (vitstr) {                     // no decoder: neutral values keep the (unused) decoder workspace sizes sane
     e->cfg.dec_num_heads = D / 32;
     e->cfg.dec_mlp_ratio = 1;
@@ -1120,25 +1136,26 @@ int parseq_finalize(parseq_engine* e, parseq_stream_t stream) {
   float* ctx = nullptr;
   __nv_bfloat16* ctxn = nullptr;
   __nv_bfloat16* qn = nullptr;
-  PQ_TRY(dev_alloc(&ctx, rows * D));
-  PQ_TRY(dev_alloc(&ctxn, rows * D));
-  PQ_TRY(dev_alloc(&qn, 1ll * L * D));
+  int r = dev_alloc(&ctx, rows * D);
+  if (r == PARSEQ_OK) r = dev_alloc(&ctxn, rows * D);
+  if (r == PARSEQ_OK) r = dev_alloc(&qn, 1ll * L * D);
+  if (r != PARSEQ_OK) { cudaFree(ctx); cudaFree(ctxn); cudaFree(qn); return r; }
   pq::build_ctx_rows_kernel<<<1024, 256, 0, st>>>(e->wf("text_embed.embedding.weight"), e->wf("pos_queries"), ctx, L, V, D,
                                                   std::sqrt(static_cast<float>(D)));
-  PQ_CUDA(cudaGetLastError());
-  int r = layernorm_launch(ctx, e->wf(Ly + "norm_c.weight"), e->wf(Ly + "norm_c.bias"), 1e-5f, static_cast<int>(rows), D,
+  if (cudaGetLastError() != cudaSuccess) r = fail(PARSEQ_ERR_CUDA, "build_ctx_rows_kernel launch");
+  if (r == PARSEQ_OK) r = layernorm_launch(e->lo, ctx, e->wf(Ly + "norm_c.weight"), e->wf(Ly + "norm_c.bias"), 1e-5f, static_cast<int>(rows), D,
                            ctxn, nullptr, st);
   // content K/V for every (position, token): rows D..3D-1 of self_attn.in_proj (enc-dec packed projection)
   if (r == PARSEQ_OK)
-    r = gemm_launch(ctxn, D, e->wb(Ly + "self_attn.in_proj_weight") + 1ll * D * D, D,
+    r = gemm_launch(e->lo, ctxn, D, e->wb(Ly + "self_attn.in_proj_weight") + 1ll * D * D, D,
                     e->wf(Ly + "self_attn.in_proj_bias") + D, static_cast<int>(rows), 2 * D, D, pq::EPI_BF16, 1.0f, nullptr,
                     0, 0, e->kvtab, 2 * D, st);
   // query projections of the (input independent) position queries, pre-scaled by 1/sqrt(head_dim)
   if (r == PARSEQ_OK)
-    r = layernorm_launch(e->wf("pos_queries"), e->wf(Ly + "norm_q.weight"), e->wf(Ly + "norm_q.bias"), 1e-5f, L, D, qn,
+    r = layernorm_launch(e->lo, e->wf("pos_queries"), e->wf(Ly + "norm_q.weight"), e->wf(Ly + "norm_q.bias"), 1e-5f, L, D, qn,
                          nullptr, st);
   if (r == PARSEQ_OK)
-    r = gemm_launch(qn, D, e->wb(Ly + "self_attn.in_proj_weight"), D, e->wf(Ly + "self_attn.in_proj_bias"), L, D, D,
+    r = gemm_launch(e->lo, qn, D, e->wb(Ly + "self_attn.in_proj_weight"), D, e->wf(Ly + "self_attn.in_proj_bias"), L, D, D,
                     pq::EPI_F32, 1.0f / std::sqrt(static_cast<float>(e->dh_dec)), nullptr, 0, 0, e->qs, D, st);
   cudaError_t ce = cudaStreamSynchronize(st);
   cudaFree(ctx);
@@ -1154,6 +1171,7 @@ int parseq_forward(parseq_engine* e, const parseq_forward_args* a, const float* 
                    int32_t* steps, parseq_stream_t stream) {
   if (e == nullptr || a == nullptr || images == nullptr || logits == nullptr)
     return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken) return fail(PARSEQ_ERR_STATE, "engine workspace is gone (a failed resize): destroy the handle");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
   if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
   if (a->batch == 0) return PARSEQ_OK;
@@ -1165,6 +1183,7 @@ int parseq_forward_host(parseq_engine* e, const parseq_forward_args* a, const fl
                         int32_t* ids_host, int32_t* steps_host, parseq_stream_t stream) {
   if (e == nullptr || a == nullptr || images_host == nullptr || logits_host == nullptr)
     return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken) return fail(PARSEQ_ERR_STATE, "engine workspace is gone (a failed resize): destroy the handle");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
   if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
   if (a->batch == 0) return PARSEQ_OK;
@@ -1181,6 +1200,7 @@ int parseq_forward_u8(parseq_engine* e, const parseq_forward_args* a, const uint
                       int32_t* steps, parseq_stream_t stream) {
   if (e == nullptr || a == nullptr || images_hwc == nullptr || logits == nullptr)
     return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken) return fail(PARSEQ_ERR_STATE, "engine workspace is gone (a failed resize): destroy the handle");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
   if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
   if (a->batch == 0) return PARSEQ_OK;
@@ -1192,6 +1212,7 @@ int parseq_forward_host_u8(parseq_engine* e, const parseq_forward_args* a, const
                            int32_t* ids_host, int32_t* steps_host, parseq_stream_t stream) {
   if (e == nullptr || a == nullptr || images_hwc_host == nullptr || logits_host == nullptr)
     return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken) return fail(PARSEQ_ERR_STATE, "engine workspace is gone (a failed resize): destroy the handle");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called after the last weight update");
   if (a->batch < 0 || a->refine_iters < 0) return fail(PARSEQ_ERR_INVALID_ARG, "negative batch / refine_iters");
   if (a->batch == 0) return PARSEQ_OK;
@@ -1216,6 +1237,7 @@ int parseq_postprocess(const float* logits, int32_t batch, int32_t num_steps, in
 
 int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* memory, parseq_stream_t stream) {
   if (e == nullptr || images == nullptr || memory == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken) return fail(PARSEQ_ERR_STATE, "engine workspace is gone (a failed resize): destroy the handle");
   if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called");
   PQ_CUDA(cudaSetDevice(e->cfg.device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
@@ -1236,25 +1258,30 @@ int64_t parseq_kernel_launches(const parseq_engine* e) { return e ? e->launches 
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (name == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null option");
   const std::string n(name);
+  // launch options: per handle; with a NULL handle they set the process defaults used by the bare kernel exports
+  // (parseq_gemm_bf16 & co.) and inherited by handles created afterwards
+  LaunchOpts& lo = e ? e->lo : g_default_opts;
   if (n == "block_n") {
     if (value != 0 && value != 64 && value != 128 && value != 192 && value != 256)
       return fail(PARSEQ_ERR_INVALID_ARG, "block_n: 0/64/128/192/256");
-    g_block_n_override = static_cast<int>(value);
+    lo.block_n = static_cast<int>(value);
+    if (e) drop_graphs(e);
     return PARSEQ_OK;
   }
-  if (n == "attn_impl") { g_attn_impl = value != 0 ? 1 : 0; if (e) drop_graphs(e); return PARSEQ_OK; }
-  if (n == "pdl") { g_use_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
-  if (n == "tma_epilogue") { g_no_tma_epilogue = (value == 0); return PARSEQ_OK; }
+  if (n == "attn_impl") { lo.attn_impl = value != 0 ? 1 : 0; if (e) drop_graphs(e); return PARSEQ_OK; }
+  if (n == "pdl") { lo.use_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
+  if (n == "tma_epilogue") { lo.no_tma_epilogue = (value == 0); if (e) drop_graphs(e); return PARSEQ_OK; }
+  if (n == "gemm_stages") { lo.gemm_stages = value > 0 ? static_cast<int>(value) : 0; if (e) drop_graphs(e); return PARSEQ_OK; }
+  if (n == "cta_group") {
+    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "cta_group: 0 (auto) / 1 / 2");
+    lo.cta_group = static_cast<int>(value);
+    if (e) drop_graphs(e);
+    return PARSEQ_OK;
+  }
   if (n == "fuse_ln") {
     if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
     e->fuse_ln = static_cast<int>(value) & 7;
     drop_graphs(e);
-    return PARSEQ_OK;
-  }
-  if (n == "gemm_stages") { g_gemm_stages = value > 0 ? static_cast<int>(value) : 0; return PARSEQ_OK; }
-  if (n == "cta_group") {
-    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "cta_group: 0 (auto) / 1 / 2");
-    g_cta_group_override = static_cast<int>(value);
     return PARSEQ_OK;
   }
   if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
@@ -1269,16 +1296,28 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (n == "ar_kernel") { e->use_ar_kernel = value != 0; drop_graphs(e); return PARSEQ_OK; }
   if (n == "chunk" || n == "max_batch" || n == "dec_chunk") {
     if (value <= 0 || value > 8192) return fail(PARSEQ_ERR_INVALID_ARG, "chunk / max_batch / dec_chunk out of range");
+    // validate the new sizes BEFORE touching the workspace
+    int chunk = e->chunk, dec_chunk = e->dec_chunk, max_batch = e->max_batch;
+    if (n == "chunk") chunk = static_cast<int>(value);
+    else if (n == "dec_chunk") dec_chunk = static_cast<int>(value);
+    else { max_batch = static_cast<int>(value); chunk = max_batch; }
+    if (chunk > max_batch) chunk = max_batch;
+    if (dec_chunk > max_batch) dec_chunk = max_batch;
+    if ((max_batch + dec_chunk - 1) / dec_chunk > 64) return fail(PARSEQ_ERR_INVALID_ARG, "too many decoder chains");
     PQ_CUDA(cudaSetDevice(e->cfg.device));
     PQ_CUDA(cudaDeviceSynchronize());
+    const int old_chunk = e->chunk, old_dec = e->dec_chunk, old_max = e->max_batch;
     free_workspace(e);
-    if (n == "chunk") e->chunk = static_cast<int>(value);
-    else if (n == "dec_chunk") e->dec_chunk = static_cast<int>(value);
-    else { e->max_batch = static_cast<int>(value); e->chunk = e->max_batch; }
-    if (e->chunk > e->max_batch) e->chunk = e->max_batch;
-    if (e->dec_chunk > e->max_batch) e->dec_chunk = e->max_batch;
-    if ((e->max_batch + e->dec_chunk - 1) / e->dec_chunk > 64) return fail(PARSEQ_ERR_INVALID_ARG, "too many decoder chains");
-    return alloc_workspace(e);
+    e->chunk = chunk; e->dec_chunk = dec_chunk; e->max_batch = max_batch;
+    int r = alloc_workspace(e);
+    if (r != PARSEQ_OK) {            // out of memory: back to the sizes that worked
+      const std::string why = g_last_error;
+      free_workspace(e);
+      e->chunk = old_chunk; e->dec_chunk = old_dec; e->max_batch = old_max;
+      if (alloc_workspace(e) != PARSEQ_OK) { e->finalized = false; free_workspace(e); e->broken = true; }
+      return fail(r, why);
+    }
+    return PARSEQ_OK;
   }
   return fail(PARSEQ_ERR_INVALID_ARG, "unknown option: " + n);
 }
@@ -1310,20 +1349,21 @@ int parseq_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, con
                      int mode, float alpha, const float* resid, int64_t ldr, int resid_mod, void* out, int64_t ldo,
                      parseq_stream_t stream) {
   if (mode < 0 || mode > 2) return fail(PARSEQ_ERR_INVALID_ARG, "bad epilogue mode");
-  return gemm_launch(A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo,
+  return gemm_launch(g_default_opts, A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo,
                      reinterpret_cast<cudaStream_t>(stream));
 }
 int parseq_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int D, int K,
                          float* x_inout, const float* gamma, const float* beta, float eps, void* xn_bf16,
                          parseq_stream_t stream) {
-  return gemm_ln_launch(A, lda, W, ldw, bias, M, D, K, x_inout, gamma, beta, eps, xn_bf16, reinterpret_cast<cudaStream_t>(stream));
+  return gemm_ln_launch(g_default_opts, A, lda, W, ldw, bias, M, D, K, x_inout, gamma, beta, eps, xn_bf16, reinterpret_cast<cudaStream_t>(stream));
 }
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y_bf16,
                           float* y_f32_or_null, parseq_stream_t stream) {
-  return layernorm_launch(x, gamma, beta, eps, M, D, y_bf16, y_f32_or_null, reinterpret_cast<cudaStream_t>(stream));
+  return layernorm_launch(g_default_opts, x, gamma, beta, eps, M, D, y_bf16, y_f32_or_null, reinterpret_cast<cudaStream_t>(stream));
 }
 int parseq_enc_attention(const void* qkv_bf16, int B, int T, int D, int heads, void* out_bf16, parseq_stream_t stream) {
-  return enc_attention_launch(qkv_bf16, B, T, D, heads, out_bf16, reinterpret_cast<cudaStream_t>(stream));
+  PQ_TRY(ensure_sm_count(g_default_opts));
+  return enc_attention_launch(g_default_opts, qkv_bf16, B, T, D, heads, out_bf16, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
