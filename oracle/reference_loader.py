@@ -2,7 +2,8 @@
 present in the build container only) under the timm shim.  TEST INFRASTRUCTURE ONLY: used by
 oracle/make_golden.py and by CPU tests that are skipped when /root/reference is absent.
 
-Nothing in `-m gpu` tests, smoke() or bench.py calls this (the GPU box has no /root/reference).
+On the GPU box /root/reference does not exist: there the byte-compiled copy `oracle/_ref/` (oracle/build_ref.py) is
+imported instead, and only by bench.py's CPU legs (`--impl reference`, `cpu_baseline`).
 """
 from __future__ import annotations
 
@@ -11,10 +12,23 @@ import os
 import sys
 
 REF_ROOT = os.environ.get("PARSEQ_REFERENCE_ROOT", "/root/reference")
+# byte-compiled copy of the same modules made by oracle/build_ref.py (travels to the GPU box; binaries only)
+_REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+if not os.path.isfile(os.path.join(REF_ROOT, "strhub/models/parseq/model.py")) and \
+        os.path.isfile(os.path.join(_REF_PYC, "strhub/models/parseq/model.pyc")):
+    REF_ROOT = _REF_PYC
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "strhub/models/parseq/model.py"))
+    return os.path.isfile(os.path.join(REF_ROOT, "strhub/models/parseq/model.py")) or \
+        os.path.isfile(os.path.join(REF_ROOT, "strhub/models/parseq/model.pyc"))
+
+
+def kind() -> str:
+    """'source' (the reference tree itself), 'pyc' (oracle/_ref, byte-compiled from it) or 'absent'."""
+    if os.path.isfile(os.path.join(REF_ROOT, "strhub/models/parseq/model.py")):
+        return "source"
+    return "pyc" if available() else "absent"
 
 
 def load_reference_classes():

@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "dec_ar.cuh"
+#include "dec_ar2.cuh"
 #include "attn_tc.cuh"
 #include "gemm_ln.cuh"
 
@@ -73,6 +74,24 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int esize, long long rows, long 
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PARSEQ_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return PARSEQ_OK;
+}
+
+// 3D bf16 tensor map [d2][d1][d0] (d0 contiguous), strides in elements, box = box_d0 x box_d1 x 1, 128B swizzle:
+// the decoder's cross K/V cache viewed as [image][key][2D] (keys past T read as zeros).
+int make_tmap3d(CUtensorMap* tm, const void* ptr, long long d0, long long d1, long long d2, long long ld1, long long ld2,
+                int box_d0, int box_d1) {
+  PQ_TRY(load_driver_api());
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ((ld1 * 2) & 15) != 0 || ((ld2 * 2) & 15) != 0)
+    return fail(PARSEQ_ERR_INVALID_ARG, "tensor map operand must be 16-byte aligned with 16-byte multiple strides");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld1) * 2u, static_cast<cuuint64_t>(ld2) * 2u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_d0), static_cast<cuuint32_t>(box_d1), 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PARSEQ_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: " + std::to_string(int(r)));
   return PARSEQ_OK;
 }
 
@@ -189,6 +208,11 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<192, 1>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<192, 2>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<384, 1>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<384, 2>())));
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<768, 1>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -367,6 +391,10 @@ struct parseq_engine {
   int dec_chunk = 128;              // images per decoder chain (each chain runs on its own stream)
   // persistent AR-loop kernel state (whole super-chunk)
   bool use_ar_kernel = true;
+  int ar_impl = 2;                  // 2: cluster-owned kernel (dec_ar2.cuh), 1: grid-barrier kernel (dec_ar.cuh)
+  pq::DecAr2Maps ar2_maps;          // TMA descriptors of the decoder weights (built by parseq_finalize) and the K/V cache
+  bool ar2_maps_ok = false;
+  int ar2_clusters[3] = {0, 0, 0};  // max co-resident clusters of the MT = 1 / 2 instantiation (index = MT)
   int fuse_ln = 3;                  // bit 0: attn.proj, bit 1: mlp.fc2 also produce the LayerNorm that follows (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
   float *ar_y = nullptr, *ar_qc = nullptr, *ar_part = nullptr;
@@ -469,6 +497,7 @@ void drop_graphs(parseq_engine* e) {
 
 void free_workspace(parseq_engine* e) {
   drop_graphs(e);
+  e->ar2_maps_ok = false;           // holds the address of the K/V cache
   void* ptrs[] = {e->a_pe, e->x, e->xn, e->qkv, e->att, e->hid, e->mem, e->ckv, e->in_images, e->out_logits, e->out_ids,
                   e->out_steps, e->in_images_u8, e->ar_sa, e->ar_ca, e->ar_hd, e->ar_y, e->ar_qc, e->ar_part, e->ar_ids, e->ar_bar, e->ar_prof};
   e->ar_part = nullptr; e->ar_prof = nullptr; e->in_images_u8 = nullptr;
@@ -492,8 +521,8 @@ void free_workspace(parseq_engine* e) {
 }
 
 // categories: 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other
-enum { CAT_ENC_GEMM = 0, CAT_ENC_ATTN = 1, CAT_LN = 2, CAT_DEC_GEMM = 3, CAT_DEC_ATTN = 4, CAT_MISC = 5, CAT_ENC_GEMM_LN = 6,
-       CAT_COUNT = 7 };
+enum { CAT_ENC_GEMM = 0, CAT_ENC_ATTN = 1, CAT_LN = 2, CAT_DEC_GEMM = 3, CAT_DEC_ATTN = 4, CAT_MISC = 5, CAT_ENC_GEMM_LN = 6, CAT_DEC_AR = 7,
+       CAT_COUNT = 8 };
 
 cudaEvent_t pool_event(parseq_engine* e) {
   if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
@@ -743,6 +772,89 @@ int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16
   return PARSEQ_OK;
 }
 
+
+// ---- cluster-owned AR kernel (dec_ar2.cuh) ----
+bool ar2_supported(const parseq_engine* e) {
+  return e->arch == 0 && e->cfg.dec_mlp_ratio == 4 && e->C <= 96 && e->T <= 256 && e->dh_dec == 32;
+}
+// weight descriptors: once per weight set (parseq_finalize); K/V cache descriptor: once per workspace
+int ar2_build_maps(parseq_engine* e) {
+  const int D = e->D;
+  const std::string Ly = "decoder.layers.0.";
+  const int DS = D / 8, MS = e->Md / 8;
+  const int NC1 = (MS % 128 == 0) ? 128 : 96, NC2 = (D % 128 == 0) ? 128 : 96;
+  PQ_TRY(make_tmap(&e->ar2_maps.wo_s, e->w(Ly + "self_attn.out_proj.weight"), 2, D, D, D, 64, DS));
+  PQ_TRY(make_tmap(&e->ar2_maps.wq_c, e->w(Ly + "cross_attn.in_proj_weight"), 2, D, D, D, 64, DS));
+  PQ_TRY(make_tmap(&e->ar2_maps.wo_c, e->w(Ly + "cross_attn.out_proj.weight"), 2, D, D, D, 64, DS));
+  PQ_TRY(make_tmap(&e->ar2_maps.w1, e->w(Ly + "linear1.weight"), 2, e->Md, D, D, 64, NC1));
+  PQ_TRY(make_tmap(&e->ar2_maps.w2, e->w(Ly + "linear2.weight"), 2, D, e->Md, e->Md, 64, NC2));
+  PQ_TRY(make_tmap(&e->ar2_maps.wh, e->w("head.weight"), 2, e->C, D, D, 64, 96));
+  const int tbox = e->T <= 64 ? 64 : 128;
+  PQ_TRY(make_tmap3d(&e->ar2_maps.ckv, e->ckv, 2ll * D, e->T, e->max_batch, 2ll * D, 2ll * D * e->T, 64, tbox));
+  e->ar2_maps_ok = true;
+  return PARSEQ_OK;
+}
+template <int D, int MT>
+int ar2_launch(parseq_engine* e, const pq::DecAr2Params& p, int ncl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ncl * pq::A2_CS));
+  cfg.blockDim = dim3(pq::A2_THREADS);
+  cfg.dynamicSmemBytes = pq::dec_ar2_smem_bytes<D, MT>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pq::A2_CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::dec_ar2_kernel<D, MT>, e->ar2_maps, p));
+  return PARSEQ_OK;
+}
+template <int D, int MT>
+int ar2_max_clusters(parseq_engine* e) {
+  if (e->ar2_clusters[MT] > 0) return e->ar2_clusters[MT];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(e->lo.sm_count / pq::A2_CS * pq::A2_CS));
+  cfg.blockDim = dim3(pq::A2_THREADS);
+  cfg.dynamicSmemBytes = pq::dec_ar2_smem_bytes<D, MT>();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pq::A2_CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, pq::dec_ar2_kernel<D, MT>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = e->lo.sm_count / (2 * pq::A2_CS);       // conservative: two clusters of 8 per GPC pair
+  }
+  e->ar2_clusters[MT] = n;
+  return n;
+}
+// images per cluster: spread the batch over the clusters that can be co-resident (never more than 16 MT rows each)
+template <int D>
+int ar2_dispatch(parseq_engine* e, pq::DecAr2Params& p, cudaStream_t st) {
+  constexpr bool kHas2 = (D != 768);            // two m16 tiles of D = 768 rows do not fit shared memory
+  const int max1 = ar2_max_clusters<D, 1>(e);
+  int per = (p.B + max1 - 1) / max1;
+  if (per <= 16 || !kHas2) {
+    if (per > 16) per = 16;
+    p.per = per;
+    return ar2_launch<D, 1>(e, p, (p.B + per - 1) / per, st);
+  }
+  if constexpr (kHas2) {
+    const int max2 = ar2_max_clusters<D, 2>(e);
+    per = (p.B + max2 - 1) / max2;
+    if (per > 32) per = 32;
+    if (per < 17) per = 17;
+    p.per = per;
+    return ar2_launch<D, 2>(e, p, (p.B + per - 1) / per, st);
+  }
+  return PARSEQ_OK;
+}
+
 // The whole AR loop (model.py:119-147) of B images in one persistent launch (csrc/dec_ar.cuh).
 int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, float* logits, int* steps, cudaStream_t st) {
   const int D = e->D;
@@ -750,6 +862,39 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
   const bool testing = a->max_length < 0;
   PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, e->ar_ids, B, 32, e->V - 2, e->V - 1));
   e->launches++;
+  if (e->ar_impl == 2 && ar2_supported(e)) {
+    if (!e->ar2_maps_ok) PQ_TRY(ar2_build_maps(e));
+    pq::DecAr2Params q;
+    q.B = B; q.L = L; q.V = e->V; q.C = e->C; q.T = e->T; q.per = 0;
+    q.tbox = e->T <= 64 ? 64 : 128; q.tb = (e->T + 127) / 128;
+    q.qscale = 1.0f / std::sqrt(static_cast<float>(e->dh_dec));
+    q.qs = e->qs; q.kvtab = e->kvtab; q.posq = e->wf("pos_queries");
+    q.bo_s = e->wf(Ly + "self_attn.out_proj.bias"); q.bq_c = e->wf(Ly + "cross_attn.in_proj_bias");
+    q.bo_c = e->wf(Ly + "cross_attn.out_proj.bias"); q.b1 = e->wf(Ly + "linear1.bias"); q.b2 = e->wf(Ly + "linear2.bias");
+    q.bh = e->wf("head.bias");
+    q.g1 = e->wf(Ly + "norm1.weight"); q.be1 = e->wf(Ly + "norm1.bias");
+    q.g2 = e->wf(Ly + "norm2.weight"); q.be2 = e->wf(Ly + "norm2.bias");
+    q.g3 = e->wf("decoder.norm.weight"); q.be3 = e->wf("decoder.norm.bias");
+    q.ids = e->ar_ids; q.ids_ld = 32; q.logits = logits;
+    q.forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
+    q.forced_ld = L;
+    q.prof = e->ar_prof_on ? e->ar_prof : nullptr;
+    {
+      const double macs = static_cast<double>(B) * L * (3.0 * D * D + 2.0 * D * e->Md + 1.0 * e->C * D + 2.0 * e->T * D);
+      TimedScope ts(e, st, CAT_DEC_AR, 2.0 * macs);
+      switch (D) {
+        case 192: PQ_TRY(ar2_dispatch<192>(e, q, st)); break;
+        case 384: PQ_TRY(ar2_dispatch<384>(e, q, st)); break;
+        case 768: PQ_TRY(ar2_dispatch<768>(e, q, st)); break;
+        default: return fail(PARSEQ_ERR_UNSUPPORTED, "dec_ar2: embed_dim must be 192, 384 or 768");
+      }
+    }
+    if (testing && steps != nullptr) {
+      PQ_TRY(launch_k(e->lo, pq::ar_steps_kernel, dim3(1), dim3(256), 0, st, static_cast<const int*>(e->ar_ids), 32, B, L, 0, steps));
+      e->launches++;
+    }
+    return PARSEQ_OK;
+  }
   PQ_CUDA(cudaMemsetAsync(e->ar_bar, 0, 64, st));
   pq::DecArParams p;
   p.B = B; p.L = L; p.Md = e->Md; p.V = e->V; p.C = e->C; p.T = e->T; p.heads = e->cfg.dec_num_heads;
@@ -774,7 +919,7 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
   {
     // per image and step: 3 D^2 (self out, cross q, cross out) + 2 D Md (MLP) + C D (head) + attention dots
     const double macs = static_cast<double>(B) * L * (3.0 * D * D + 2.0 * D * e->Md + 1.0 * e->C * D + 2.0 * e->T * D);
-    TimedScope ts(e, st, CAT_DEC_GEMM, 2.0 * macs);
+    TimedScope ts(e, st, CAT_DEC_AR, 2.0 * macs);
     const dim3 grid(static_cast<unsigned>(e->lo.sm_count)), block(pq::DEC_THREADS);
     switch (D) {
       case 192:
@@ -1163,6 +1308,8 @@ int parseq_finalize(parseq_engine* e, parseq_stream_t stream) {
   cudaFree(qn);
   if (r != PARSEQ_OK) return r;
   if (ce != cudaSuccess) return fail(PARSEQ_ERR_CUDA, std::string("finalize: ") + cudaGetErrorString(ce));
+  e->ar2_maps_ok = false;
+  if (ar2_supported(e)) PQ_TRY(ar2_build_maps(e));
   e->finalized = true;
   return PARSEQ_OK;
 }
@@ -1293,7 +1440,13 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   }
   if (n == "use_graph") { e->use_graph = value != 0; return PARSEQ_OK; }
   if (n == "ar_prof") { e->ar_prof_on = value != 0; drop_graphs(e); return PARSEQ_OK; }
-  if (n == "ar_kernel") { e->use_ar_kernel = value != 0; drop_graphs(e); return PARSEQ_OK; }
+  if (n == "ar_kernel") {           // 0: AR loop as separate kernels, 1: grid-barrier kernel (dec_ar.cuh), 2: cluster kernel
+    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "ar_kernel: 0 / 1 / 2");
+    e->use_ar_kernel = value != 0;
+    e->ar_impl = value == 1 ? 1 : 2;
+    drop_graphs(e);
+    return PARSEQ_OK;
+  }
   if (n == "chunk" || n == "max_batch" || n == "dec_chunk") {
     if (value <= 0 || value > 8192) return fail(PARSEQ_ERR_INVALID_ARG, "chunk / max_batch / dec_chunk out of range");
     // validate the new sizes BEFORE touching the workspace

@@ -138,7 +138,7 @@ class Engine:
     def set_option(self, name: str, value: int):
         check(self.lib, self.lib.parseq_set_option(self.handle, name.encode(), int(value)))
 
-    TIMING_CATEGORIES = ("enc_gemm", "enc_attn", "layernorm", "dec_gemm", "dec_attn", "other", "enc_gemm_ln")
+    TIMING_CATEGORIES = ("enc_gemm", "enc_attn", "layernorm", "dec_gemm", "dec_attn", "other", "enc_gemm_ln", "dec_ar")
 
     def get_timing(self):
         out = {}
