@@ -30,7 +30,8 @@ struct DecArParams {
   const __nv_bfloat16 *Wo_s, *Wq_c, *Wo_c, *W1, *W2, *Wh;
   const float *bo_s, *bq_c, *bo_c, *b1, *b2, *bh;
   const float *g1, *be1, *g2, *be2, *g3, *be3;
-  const __nv_bfloat16* ckv;       // [B, T, 2D]
+  const __nv_bfloat16* ckv;       // column-blocked [2D/64][kv_rows][64], row = image * T + key (ptx.cuh: blocked_off)
+  long long kv_rows;
   int* ids;                       // [B, ids_ld]: ids[:,0] = BOS on entry
   int ids_ld;
   __nv_bfloat16 *sa, *ca, *hd;    // [B, D], [B, D], [B, Md]
@@ -412,10 +413,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
     // ---------------- P4: cross-attention, warp per (image, head), T <= 128*TB keys ----------------
     for (int item = gwarp; item < p.B * p.heads; item += nwarps) {
       const int b = item / p.heads, h = item % p.heads;
-      const __nv_bfloat16* kvb = p.ckv + static_cast<long long>(b) * p.T * 2 * D;
+      const long long row_b = static_cast<long long>(b) * p.T;
       // lane = (key group kg = lane>>2, 8-channel chunk cc = lane&3) for the 16-byte V loads
       const int kg = lane >> 2, cc = lane & 3;
-      const __nv_bfloat16* vb = kvb + D + h * 32 + cc * 8;
+      const __nv_bfloat16* kb0 = p.ckv + blocked_off(p.kv_rows, row_b, h * 32);                 // + key * 64
+      const __nv_bfloat16* vb = p.ckv + blocked_off(p.kv_rows, row_b, D + h * 32 + cc * 8);     // + key * 64
       const float qv = p.qc[static_cast<long long>(b) * D + h * 32 + lane];
       float sc[4 * TB];
       uint4 vv[16];
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
         for (int r = 0; r < 4; ++r) {
           const int key = blk * 128 + r * 32 + lane;
           if (key < p.T) {
-            const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * D + h * 32);
+            const uint4* kr = reinterpret_cast<const uint4*>(kb0 + static_cast<long long>(key) * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 u = __ldg(kr + j);
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int key = i * 8 + kg;
-            vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
+            vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 64)) : make_uint4(0u, 0u, 0u, 0u);
           }
         }
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_ar_kernel(const DecArParam
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int key = blk * 128 + i * 8 + kg;
-            vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 2 * D)) : make_uint4(0u, 0u, 0u, 0u);
+            vv[i] = (key < p.T) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 64)) : make_uint4(0u, 0u, 0u, 0u);
           }
         }
 #pragma unroll

@@ -117,8 +117,9 @@ struct A2Cfg {
   static constexpr int IDS_BYTES = ROWS * 32 * 4;
   static constexpr int SLOG_BYTES = ROWS * A2_SLOG_LD * 4;
   static constexpr int MISC_BYTES = 1024;              // mbarriers, row statistics
-  static constexpr int FIXED = A_BYTES + R_BYTES + HD_BYTES + Y_BYTES + Q_BYTES + P_BYTES + CA_BYTES + ST_BYTES + RED_BYTES +
-                               IDS_BYTES + SLOG_BYTES + MISC_BYTES + ROWS * 8;
+  static constexpr int PL_BYTES = P_BYTES > SLOG_BYTES ? P_BYTES : SLOG_BYTES;   // P (cross-attention) and the staged logits (head) share
+  static constexpr int FIXED = A_BYTES + R_BYTES + HD_BYTES + Y_BYTES + Q_BYTES + PL_BYTES + CA_BYTES + ST_BYTES + RED_BYTES +
+                               IDS_BYTES + MISC_BYTES + ROWS * 8;
   static constexpr int NSLOT_RAW = (232448 - 1024 - FIXED) / A2_SLOT;
   static constexpr int NSLOT = NSLOT_RAW > 8 ? 8 : NSLOT_RAW;
   static constexpr int SMEM = 1024 + NSLOT * A2_SLOT + FIXED;
@@ -139,14 +140,14 @@ struct A2Ring {
   uint64_t* full;
   const DecAr2Maps* maps;
   int rank, n_own, img0, per_here;     // img0: first image of the cluster
-  int tbox, tb;
+  int tbox, tb, T;
   int items_per_step, total;
   int seg_b, seg_c, seg_d, seg_e, seg_f, seg_g;   // first item index of each segment
   int cons, prod;
 
   __device__ void init(uint8_t* slots_, uint64_t* full_, const DecAr2Maps* maps_, int rank_, int n_own_, int img0_, int tbox_,
-                       int tb_, int steps) {
-    slots = slots_; full = full_; maps = maps_; rank = rank_; n_own = n_own_; img0 = img0_; tbox = tbox_; tb = tb_;
+                       int tb_, int T_, int steps) {
+    slots = slots_; full = full_; maps = maps_; rank = rank_; n_own = n_own_; img0 = img0_; tbox = tbox_; tb = tb_; T = T_;
     seg_b = Cfg::NSL_S;
     seg_c = 2 * Cfg::NSL_S;
     seg_d = seg_c + n_own * 2 * Cfg::KT * tb;
@@ -164,9 +165,7 @@ struct A2Ring {
     mbar_expect_tx(bar, static_cast<uint32_t>(n * Cfg::DS * 128));
     for (int i = 0; i < n; ++i) tma_load_2d(dst + i * Cfg::DS * 128, m, bar, (k0 + i) * 64, rank * Cfg::DS);
   }
-  __device__ void issue(int idx) {       // one thread
-    const int it = idx % items_per_step;
-    const int s = idx % Cfg::NSLOT;
+  __device__ void issue(int it, int s) {       // one thread; it = item index inside the step, s = slot
     uint8_t* dst = slots + s * A2_SLOT;
     uint64_t* bar = &full[s];
     if (it < seg_b) { issue_slice(&maps->wo_s, it, dst, bar); return; }
@@ -179,7 +178,9 @@ struct A2Ring {
       const int oi = j >> 1;
       const int img = img0 + rank + A2_CS * oi;
       mbar_expect_tx(bar, static_cast<uint32_t>(tbox * 128));
-      tma_load_3d(dst, &maps->ckv, bar, kv * D + kb * 64, t * 128, img);
+      // column-blocked cache [2D/64][rows][64], row = image * T + key: one contiguous tbox x 128 B run (rows past the
+      // image's T keys belong to the next image or are out of bounds: masked by the softmax)
+      tma_load_3d(dst, &maps->ckv, bar, 0, img * T + t * 128, kv * Cfg::KT + kb);
       return;
     }
     if (it < seg_e) { issue_slice(&maps->wo_c, it - seg_d, dst, bar); return; }
@@ -198,8 +199,16 @@ struct A2Ring {
     mbar_expect_tx(bar, 96 * 128);       // head: [96 x 64] (row 95.. zero-filled by the tensor map bounds)
     tma_load_2d(dst, &maps->wh, bar, (it - seg_g) * 64, 0);
   }
-  __device__ void prologue() {           // thread 0
-    for (; prod < Cfg::NSLOT && prod < total; ++prod) issue(prod);
+  // `prod` (items issued so far), its position inside the step and its slot advance identically in every thread; the
+  // thread that issues rotates over the warps so that no warp carries the serial TMA-issue cost of every item
+  int prod_it, prod_slot;
+  __device__ void prologue() {           // all threads (thread 0 issues)
+    prod_it = 0; prod_slot = 0;
+    for (; prod < Cfg::NSLOT && prod < total; ++prod) {
+      if (threadIdx.x == 0) issue(prod_it, prod_slot);
+      if (++prod_it == items_per_step) prod_it = 0;
+      if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
+    }
   }
   __device__ __forceinline__ const uint8_t* wait() {          // all threads
     const int s = cons % Cfg::NSLOT;
@@ -209,10 +218,10 @@ struct A2Ring {
   __device__ __forceinline__ void release() {                  // all threads; the slot just consumed is refilled
     __syncthreads();
     ++cons;
-    if (threadIdx.x == 0) {
-      if (prod < total) { issue(prod); }
-      ++prod;
-    }
+    if (prod < total && threadIdx.x == ((prod & 7) << 5)) issue(prod_it, prod_slot);
+    ++prod;
+    if (++prod_it == items_per_step) prod_it = 0;
+    if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
   }
 };
 
@@ -255,12 +264,12 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   uint8_t* s_hd = sm;                                           sm += Cfg::HD_BYTES;
   float* s_y = reinterpret_cast<float*>(sm);                    sm += Cfg::Y_BYTES;     // [ROWS][DS]
   float* s_q = reinterpret_cast<float*>(sm);                    sm += Cfg::Q_BYTES;     // [OWN][D]
-  uint8_t* s_p = sm;                                            sm += Cfg::P_BYTES;     // hi | lo
+  uint8_t* s_p = sm;                                            sm += Cfg::PL_BYTES;    // hi | lo; the head stages its logits here
   __nv_bfloat16* s_ca = reinterpret_cast<__nv_bfloat16*>(sm);   sm += Cfg::CA_BYTES;
   float2* s_st = reinterpret_cast<float2*>(sm);                 sm += Cfg::ST_BYTES;    // [8 src][ROWS] (mean, M2)
   float* s_red = reinterpret_cast<float*>(sm);                  sm += Cfg::RED_BYTES;   // [2][8 warps][16 MH]
   int* s_ids = reinterpret_cast<int*>(sm);                      sm += Cfg::IDS_BYTES;   // [ROWS][32]
-  float* s_log = reinterpret_cast<float*>(sm);                  sm += Cfg::SLOG_BYTES;
+  float* s_log = reinterpret_cast<float*>(s_p);
   float2* s_mr = reinterpret_cast<float2*>(sm);                 sm += ROWS * 8;         // per row (mean, rstd)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm);
 
@@ -289,9 +298,9 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     s_ids[i] = (r < nrows) ? p.ids[static_cast<long long>(img0 + r) * p.ids_ld + c] : 0;
   }
   A2Ring<D, MT> ring;
-  ring.init(s_ring, s_bar, &maps, rank, n_own, img0, p.tbox, p.tb, p.L);
+  ring.init(s_ring, s_bar, &maps, rank, n_own, img0, p.tbox, p.tb, p.T, p.L);
   __syncthreads();
-  if (tid == 0) ring.prologue();
+  ring.prologue();
   cluster_sync_relacq();              // every CTA of the cluster is running (remote stores are legal) and zero-filled
 
   // ---- helpers -------------------------------------------------------------------------------------------------

@@ -228,9 +228,10 @@ int init_kernel_attributes() {
   return PARSEQ_OK;
 }
 
+// blocked_rows > 0: `out` is a column-blocked bf16 buffer [N/64][blocked_rows][64] (ptx.cuh: blocked_off); ldo is ignored
 int gemm_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N,
                 int K, int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
-                cudaStream_t st) {
+                cudaStream_t st, long long blocked_rows = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm: empty problem");
   PQ_TRY(ensure_sm_count(lo));
   // Tile choice from tests/bench_gemm.py on B200 (profiles/r1_gemm_microbench*.txt): single-CTA 128 x 256 tiles win
@@ -264,7 +265,12 @@ int gemm_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, lon
     else if (resid == nullptr) p.tma_out = 1;
     else if (resid == out && ldr == ldo && resid_mod == 0) p.tma_out = 2;
   }
-  if (p.tma_out == 3) PQ_TRY(make_tmap(&tc, out, 2, M, N, ldo, 64, 32));
+  if (blocked_rows > 0) {
+    if (mode == pq::EPI_F32 || N % 64 != 0 || blocked_rows < M || (reinterpret_cast<uintptr_t>(out) & 15u) != 0)
+      return fail(PARSEQ_ERR_INVALID_ARG, "gemm: blocked output needs a bf16 epilogue, N % 64 == 0 and rows >= M");
+    p.tma_out = 4;
+    PQ_TRY(make_tmap3d(&tc, out, 64, blocked_rows, N / 64, 64, 64 * blocked_rows, 64, 32));
+  } else if (p.tma_out == 3) PQ_TRY(make_tmap(&tc, out, 2, M, N, ldo, 64, 32));
   else if (p.tma_out != 0) PQ_TRY(make_tmap(&tc, out, 4, M, N, ldo, 32, 32));
   else tc = ta;
   const int tile_m = pq::GEMM_BLOCK_M * CG;
@@ -543,9 +549,9 @@ struct TimedScope {   // records a CUDA-event pair around the launches issued in
 
 int gemm(parseq_engine* e, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N,
          int K, int mode, float alpha, const float* resid, long long ldr, int resid_mod, void* out, long long ldo,
-         cudaStream_t st) {
+         cudaStream_t st, long long blocked_rows = 0) {
   TimedScope ts(e, st, e->cur_cat == CAT_DEC_GEMM ? CAT_DEC_GEMM : CAT_ENC_GEMM, 2.0 * M * N * K);
-  return gemm_launch(e->lo, A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st);
+  return gemm_launch(e->lo, A, lda, W, ldw, bias, M, N, K, mode, alpha, resid, ldr, resid_mod, out, ldo, st, blocked_rows);
 }
 // x += A W^T + b;  y = bf16(LayerNorm(x; <ln_prefix>))  in one kernel
 int gemm_ln(parseq_engine* e, const void* A, long long lda, const std::string& lin, int M, int K, float* x,
@@ -667,7 +673,7 @@ int vitstr_tail(parseq_engine* e, int B, int L, float* logits, int* ids_out, cud
 // ---------------------------------------------------------------- one Decoder call (model.py:86-103, modules.py:55-125)
 // rows are (b, qi), qi in [0,nq); query position q0+qi; context ids[b, 0..nkeys-1].
 // Tail: LayerNorm(decoder.norm) + head + (optionally) greedy argmax -> ids_dst[b*32 + dst_off + qi] in one kernel.
-int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16* ckv, int B, int nq, int q0, int nkeys,
+int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int b_first, int B, int nq, int q0, int nkeys,
                 int mode, const int* ids, float* logits_out, long long logits_ld, int* ids_dst, int dst_off,
                 const int* forced, int forced_ld, cudaStream_t st) {
   const int D = e->D, M = B * nq;
@@ -692,12 +698,15 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16*
   PQ_TRY(gemm(e, sg.yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, sg.qc, D, st));
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
+    const long long kv_rows = 1ll * e->max_batch * e->T;
     if (e->T <= 128)
       PQ_TRY(launch_k(e->lo, pq::dec_cross_attn3_kernel<4>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
-                      static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
+                      static_cast<const float*>(sg.qc), static_cast<const __nv_bfloat16*>(e->ckv), kv_rows, b_first, e->T, D,
+                      e->cfg.dec_num_heads, nq, sg.ca));
     else
       PQ_TRY(launch_k(e->lo, pq::dec_cross_attn3_kernel<8>, dim3(B * e->cfg.dec_num_heads), dim3(128), 0, st,
-                      static_cast<const float*>(sg.qc), ckv, e->T, D, e->cfg.dec_num_heads, nq, sg.ca));
+                      static_cast<const float*>(sg.qc), static_cast<const __nv_bfloat16*>(e->ckv), kv_rows, b_first, e->T, D,
+                      e->cfg.dec_num_heads, nq, sg.ca));
   }
   PQ_TRY(gemm(e, sg.ca, D, e->w(Ly + "cross_attn.out_proj.weight"), D, e->wf(Ly + "cross_attn.out_proj.bias"), M, D, D,
               pq::EPI_F32, 1.0f, sg.y, D, 0, sg.y, D, st));
@@ -732,8 +741,9 @@ int argmax_rows(parseq_engine* e, const float* logits, int L, int B, int nrows, 
 
 // Decoder chain of one group of B <= dec_chunk images (their cross K/V is at `ckv`): AR loop / NAR pass, cloze
 // refinement, final argmax.  model.py:113-169.
-int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16* ckv, const parseq_forward_args* a, int b0,
+int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, int b_first, const parseq_forward_args* a, int b0,
                  int B, int L, float* logits, int* ids_out, int* steps, cudaStream_t st, bool ar_done) {
+  // b_first: index of the group's first image inside the super-chunk (row of the K/V cache); b0: inside the caller's batch
   const int C = e->C;
   const int bos = e->V - 2, pad = e->V - 1;
   const bool testing = a->max_length < 0;
@@ -746,7 +756,7 @@ int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16
     const int* forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
     for (int i = 0; i < L; ++i) {
       // step i: context ids[:, :i+1], query position i; the fused tail writes ids[:, i+1] = argmax (model.py:142)
-      PQ_TRY(decode_pass(e, sg, ckv, B, 1, i, i + 1, 0, sg.ids_ar, logits + static_cast<long long>(i) * C, LC,
+      PQ_TRY(decode_pass(e, sg, b_first, B, 1, i, i + 1, 0, sg.ids_ar, logits + static_cast<long long>(i) * C, LC,
                          (i + 1 < L) ? sg.ids_ar : nullptr, i + 1, forced, L, st));
     }
     if (testing && steps != nullptr) {
@@ -756,7 +766,7 @@ int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16
   } else {
     PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
     e->launches++;
-    PQ_TRY(decode_pass(e, sg, ckv, B, L, 0, 1, 0, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
+    PQ_TRY(decode_pass(e, sg, b_first, B, L, 0, 1, 0, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
   }
   for (int it = 0; it < a->refine_iters; ++it) {
     PQ_TRY(launch_k(e->lo, pq::fill_ids_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, sg.ids_ctx, B, 32, bos, pad));
@@ -766,7 +776,7 @@ int decode_stage(parseq_engine* e, parseq_engine::Stage& sg, const __nv_bfloat16
                             : nullptr;
     // ctx = [BOS, argmax(logits[:, :L-1])]  (model.py:161)
     PQ_TRY(argmax_rows(e, logits, L, B, L - 1, 0, sg.ids_ctx, 32, 1, forced, L, st));
-    PQ_TRY(decode_pass(e, sg, ckv, B, L, 0, L, 1, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
+    PQ_TRY(decode_pass(e, sg, b_first, B, L, 0, L, 1, sg.ids_ctx, logits, C, nullptr, 0, nullptr, 0, st));
   }
   if (ids_out != nullptr) PQ_TRY(argmax_rows(e, logits, L, B, L, 0, ids_out, L, 0, nullptr, 0, st));
   return PARSEQ_OK;
@@ -790,7 +800,8 @@ int ar2_build_maps(parseq_engine* e) {
   PQ_TRY(make_tmap(&e->ar2_maps.w2, e->w(Ly + "linear2.weight"), 2, D, e->Md, e->Md, 64, NC2));
   PQ_TRY(make_tmap(&e->ar2_maps.wh, e->w("head.weight"), 2, e->C, D, D, 64, 96));
   const int tbox = e->T <= 64 ? 64 : 128;
-  PQ_TRY(make_tmap3d(&e->ar2_maps.ckv, e->ckv, 2ll * D, e->T, e->max_batch, 2ll * D, 2ll * D * e->T, 64, tbox));
+  const long long kv_rows = 1ll * e->max_batch * e->T;     // column-blocked cache [2D/64][kv_rows][64]
+  PQ_TRY(make_tmap3d(&e->ar2_maps.ckv, e->ckv, 64, kv_rows, 2 * D / 64, 64, 64 * kv_rows, 64, tbox));
   e->ar2_maps_ok = true;
   return PARSEQ_OK;
 }
@@ -909,7 +920,7 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
   p.g1 = e->wf(Ly + "norm1.weight"); p.be1 = e->wf(Ly + "norm1.bias");
   p.g2 = e->wf(Ly + "norm2.weight"); p.be2 = e->wf(Ly + "norm2.bias");
   p.g3 = e->wf("decoder.norm.weight"); p.be3 = e->wf("decoder.norm.bias");
-  p.ckv = e->ckv; p.ids = e->ar_ids; p.ids_ld = 32;
+  p.ckv = e->ckv; p.kv_rows = 1ll * e->max_batch * e->T; p.ids = e->ar_ids; p.ids_ld = 32;
   p.sa = e->ar_sa; p.ca = e->ar_ca; p.hd = e->ar_hd; p.y = e->ar_y; p.qc = e->ar_qc; p.part = e->ar_part;
   p.logits = logits;
   p.forced = a->forced_ids ? a->forced_ids + static_cast<long long>(b0) * L : nullptr;
@@ -969,7 +980,10 @@ int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B,
     const std::string Ly = "decoder.layers.0.";
     const __nv_bfloat16* Wkv = e->wb(Ly + "cross_attn.in_proj_weight") + static_cast<long long>(D) * D;
     const float* bkv = e->wf(Ly + "cross_attn.in_proj_bias") + D;
-    PQ_TRY(gemm(e, e->mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, e->ckv, 2 * D, e->main));
+    // stored column-blocked [2D/64][max_batch * T][64]: an image's K (V) panel of 64 channels is one contiguous T x 128 B
+    // run - what a TMA box of the AR kernel and a head of the refine-pass attention read
+    PQ_TRY(gemm(e, e->mem, D, Wkv, D, bkv, B * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, e->ckv, 2 * D, e->main,
+                1ll * e->max_batch * T));
   }
   const bool ar_done = a->decode_ar && e->use_ar_kernel;
   if (ar_done) {
@@ -988,7 +1002,7 @@ int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B,
     const int Bs = (B - o < e->dec_chunk) ? (B - o) : e->dec_chunk;
     cudaStream_t ds = fork ? sg.stream : e->main;
     if (fork) PQ_CUDA(cudaStreamWaitEvent(ds, e->ev_enc, 0));
-    PQ_TRY(decode_stage(e, sg, e->ckv + 1ll * o * T * 2 * D, a, b0 + o, Bs, L, logits + 1ll * o * L * e->C,
+    PQ_TRY(decode_stage(e, sg, o, a, b0 + o, Bs, L, logits + 1ll * o * L * e->C,
                         ids_out ? ids_out + 1ll * o * L : nullptr, steps, ds, ar_done));
     if (fork) PQ_CUDA(cudaEventRecord(sg.ev_done, ds));
   }

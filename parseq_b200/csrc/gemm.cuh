@@ -32,6 +32,7 @@ struct GemmParams {
   int vec_ok;          // 16B-aligned rows: vector stores allowed
   int tma_out;         // 0: direct stores (fallback), 1: TMA store fp32, 2: TMA reduce-add fp32 (out += ...),
                        // 3: TMA store bf16 (mode EPI_BF16 / EPI_GELU_BF16)
+                       // 4: TMA store bf16 into a column-blocked buffer [N/64][rows][64] (3D tensor map)
   int num_m_tiles, num_n_tiles;  // in units of (128 * CG) x BLOCK_N
   int max_stages;                // 0: the full operand ring; n > 0: use only n slots (pipeline-depth experiments)
 };
@@ -130,10 +131,17 @@ __device__ __forceinline__ void epi_tma_bf16(const GemmParams& p, const CUtensor
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         float f[8];
+        if constexpr (GELU) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float a = __uint_as_float(v[jj * 8 + t]) + bb[jj * 8 + t];
-          f[t] = GELU ? gelu_erf(a) : a * p.alpha;
+          for (int t = 0; t < 8; t += 2) {                 // two columns per FFMA2 / FADD2 issue slot
+            float a0, a1;
+            f2_unpack(f2_add(f2_pack(__uint_as_float(v[jj * 8 + t]), __uint_as_float(v[jj * 8 + t + 1])),
+                             *reinterpret_cast<const unsigned long long*>(bb + jj * 8 + t)), a0, a1);
+            gelu_erf_x2(a0, a1, f[t], f[t + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f[t] = (__uint_as_float(v[jj * 8 + t]) + bb[jj * 8 + t]) * p.alpha;
         }
         q[h * 4 + jj].x = pack_bf16(f[0], f[1]); q[h * 4 + jj].y = pack_bf16(f[2], f[3]);
         q[h * 4 + jj].z = pack_bf16(f[4], f[5]); q[h * 4 + jj].w = pack_bf16(f[6], f[7]);
@@ -149,7 +157,8 @@ __device__ __forceinline__ void epi_tma_bf16(const GemmParams& p, const CUtensor
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tmC, slab, col0, row0);
+      if (p.tma_out == 4) tma_store_3d(tmC, slab, 0, row0, col0 >> 6);
+      else tma_store_2d(tmC, slab, col0, row0);
       bulk_commit_group();
     }
   }
@@ -383,7 +392,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row0 = m0 + quarter * 32;
       if (p.tma_out == 2) epi_tma_f32<BLOCK_N, true, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
       else if (p.tma_out == 1) epi_tma_f32<BLOCK_N, false, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
-      else if (p.tma_out == 3) {
+      else if (p.tma_out >= 3) {
         if (p.mode == EPI_GELU_BF16) epi_tma_bf16<BLOCK_N, true, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
         else epi_tma_bf16<BLOCK_N, false, Cfg::kSlabs>(p, &tmC, taddr, my_stage, my_bias, n0, row0, half, lane, store_it);
       } else {

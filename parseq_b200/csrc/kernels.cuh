@@ -553,8 +553,11 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
 // q fp32 [B*nq, D] pre-scaled by 1/sqrt(32); kv bf16 [B, T, 2D]; out bf16 [B*nq, D].  T <= 128, head dim 32.
 template <int NR>   // keys per lane: T <= 32 * NR (NR = 4: T <= 128, NR = 8: T <= 256)
 __global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __restrict__ q,
-                                                              const __nv_bfloat16* __restrict__ kv, int T, int D, int heads,
-                                                              int nq, __nv_bfloat16* __restrict__ out) {
+                                                              const __nv_bfloat16* __restrict__ kv, long long kv_rows,
+                                                              int b_first, int T, int D, int heads, int nq,
+                                                              __nv_bfloat16* __restrict__ out) {
+  // kv: column-blocked cross K/V cache [2D/64][kv_rows][64] (ptx.cuh: blocked_off), row = image * T + key; the
+  // queries / outputs of this launch belong to images b_first, b_first + 1, ...
   constexpr int TK = 32 * NR;
   __shared__ uint32_t sK[TK * 17];                        // bf16x2 words, pitch 17 (odd)
   __shared__ __align__(16) __nv_bfloat16 sV[TK * 32];
@@ -562,12 +565,12 @@ __global__ void __launch_bounds__(128) dec_cross_attn3_kernel(const float* __res
   grid_dep_wait();
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat16* kvb = kv + static_cast<long long>(b) * T * 2 * D;
+  const long long row_b = static_cast<long long>(b_first + b) * T;
   for (int t = tid; t < TK; t += 128) {
     uint4* vd = reinterpret_cast<uint4*>(sV + t * 32);
     if (t < T) {
-      const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + h * 32);
-      const uint4* vr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(t) * 2 * D + D + h * 32);
+      const uint4* kr = reinterpret_cast<const uint4*>(kv + blocked_off(kv_rows, row_b + t, h * 32));
+      const uint4* vr = reinterpret_cast<const uint4*>(kv + blocked_off(kv_rows, row_b + t, D + h * 32));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint4 u = __ldg(kr + j);

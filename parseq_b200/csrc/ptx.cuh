@@ -98,6 +98,11 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
@@ -260,6 +265,12 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Column-blocked activation layout [N/64 blocks][rows][64] (bf16): every [rows x 64] panel that a TMA box or a head's
+// K/V slice covers is contiguous in HBM.  Element offset of (row, col) with `rows_total` rows per block.
+__device__ __forceinline__ long long blocked_off(long long rows_total, long long row, int col) {
+  return (static_cast<long long>(col >> 6) * rows_total + row) * 64 + (col & 63);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -289,6 +300,47 @@ __device__ __forceinline__ float gelu_erf(float x) {
   // x * Phi(x) = max(x, 0) - |x| * Phi(-|x|)  (Phi(x) = 1 - Phi(-x) for x >= 0); u instead of |x| only matters
   // beyond the clamp, where the product is < 1e-15 either way
   return fmaf(-u, h, fmaxf(x, 0.0f));
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: two IEEE fp32 lanes per issue slot, bit-identical to scalar) ----
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_erf of two values at once: the same operations in the same order as gelu_erf (identical bits), with the
+// polynomial on FFMA2 - 9 issue slots per element instead of 15 (the fc1 epilogue is issue-bound)
+__device__ __forceinline__ void gelu_erf_x2(float x0, float x1, float& y0, float& y1) {
+  const float u0 = fminf(fabsf(x0), 8.5f), u1 = fminf(fabsf(x1), 8.5f);
+  const unsigned long long u = f2_pack(u0, u1);
+  const unsigned long long t = f2_fma(u, f2_pack(2.0f / 8.5f, 2.0f / 8.5f), f2_pack(-1.0f, -1.0f));
+  unsigned long long q = f2_pack(8.503329848e-03f, 8.503329848e-03f);
+  q = f2_fma(q, t, f2_pack(-2.785826938e-02f, -2.785826938e-02f));
+  q = f2_fma(q, t, f2_pack(4.857975011e-02f, 4.857975011e-02f));
+  q = f2_fma(q, t, f2_pack(-8.378244194e-02f, -8.378244194e-02f));
+  q = f2_fma(q, t, f2_pack(1.570760869e-01f, 1.570760869e-01f));
+  q = f2_fma(q, t, f2_pack(-2.896217881e-01f, -2.896217881e-01f));
+  q = f2_fma(q, t, f2_pack(-1.247551552e+01f, -1.247551552e+01f));
+  q = f2_fma(q, t, f2_pack(-2.737368526e+01f, -2.737368526e+01f));
+  q = f2_fma(q, t, f2_pack(-1.651358203e+01f, -1.651358203e+01f));
+  float q0, q1;
+  f2_unpack(q, q0, q1);
+  const unsigned long long h = f2_pack(ex2_approx(q0), ex2_approx(q1));
+  const unsigned long long r = f2_fma(f2_pack(-u0, -u1), h, f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  f2_unpack(r, y0, y1);
 }
 
 }  // namespace pq
