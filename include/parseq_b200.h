@@ -119,6 +119,22 @@ int parseq_postprocess(const float* logits, int32_t batch, int32_t num_steps, in
 int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* memory,
                   parseq_stream_t stream);
 
+/* Replaces model.PARSeq.decode (strhub/models/parseq/model.py:86-103 -> modules.py:55-125, depth-1 decoder: query stream
+ * only): tgt DEVICE int32 [N, J] context ids (tgt[:, 0] = BOS; token k >= 1 receives pos_queries[k-1], model.py:96-99),
+ * memory DEVICE fp32 [N, T, D] (what parseq_encode returns), query DEVICE fp32 [N, NQ, D] or NULL (= pos_queries[:NQ],
+ * model.py:100-101), query_mask DEVICE uint8 [NQ, J] or NULL (1 = key masked for that query: the bool `tgt_query_mask`),
+ * padding_mask DEVICE uint8 [N, J] or NULL (`tgt_padding_mask`); out DEVICE fp32 [N, NQ, D] = Decoder output including
+ * the final LayerNorm (modules.py:123-125).  1 <= J, NQ <= max_label_length + 1.  A query whose keys are all masked
+ * yields NaN, as the reference's softmax does.  `tgt_mask` (content stream) has no effect at decoder depth 1. */
+int parseq_decode(parseq_engine* e, int32_t batch, int32_t ctx_len, int32_t num_queries, const int32_t* tgt,
+                  const float* memory, const float* query, const uint8_t* query_mask, const uint8_t* padding_mask,
+                  float* out, parseq_stream_t stream);
+/* Replaces model.PARSeq.head (model.py:63: nn.Linear(embed_dim, num_tokens - 2)): x DEVICE fp32 [rows, D] ->
+ * logits DEVICE fp32 [rows, num_tokens - 2] (bf16 tensor-core operands, fp32 accumulate). */
+int parseq_head(parseq_engine* e, int32_t rows, const float* x, float* logits, parseq_stream_t stream);
+/* Replaces TokenEmbedding.forward (modules.py:175-176): out[i, :] = sqrt(D) * embedding[ids[i], :], DEVICE fp32 [n, D]. */
+int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* out, parseq_stream_t stream);
+
 /* Introspection used by bench.py / tests. */
 int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count of kernels launched */
 /* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per encoder pass inside a
@@ -126,11 +142,15 @@ int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count
  * streams), "use_graph" (0/1), "pdl" (programmatic dependent launch, 0/1), "timing" (1: record a CUDA-event pair around every launch
  * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests), "fuse_ln" (bit 0: the attention-projection GEMM, bit 1: the fc2 GEMM
  * also produces the LayerNorm that follows it, used when the batch fills the machine at least twice with 128-row tiles; bit 2:
- * for any batch; default 3; 0: separate LayerNorm kernels). */
+ * for any batch; default 3; 0: separate LayerNorm kernels), "ar_kernel" (AR loop: 2 = cluster-owned persistent kernel,
+ * default; 1 = grid-barrier persistent kernel; 0 = chain of separate kernels), "attn_impl", "cta_group", "gemm_stages",
+ * "tma_epilogue" (kernel-variant switches for tests).  Options are PER HANDLE; with e == NULL the launch options
+ * (block_n, attn_impl, pdl, tma_epilogue, gemm_stages, cta_group) set the process defaults that the stand-alone kernel
+ * entry points below use and that handles created afterwards inherit. */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of
  * category 0 encoder GEMM, 1 encoder attention, 2 LayerNorm, 3 decoder GEMM, 4 decoder attention, 5 other,
- * 6 encoder residual GEMM fused with LayerNorm. */
+ * 6 encoder residual GEMM fused with LayerNorm, 7 persistent AR-loop kernel. */
 int parseq_get_timing(parseq_engine* e, int category, double* ms, double* flops, int64_t* count);
 /* Debug: after a forward with option "ar_prof"=1, copies the [32 steps][16 slots] globaltimer (ns) stamps that block 0 of
  * the persistent AR kernel recorded at its phase boundaries. */

@@ -673,28 +673,56 @@ int vitstr_tail(parseq_engine* e, int B, int L, float* logits, int* ids_out, cud
 // ---------------------------------------------------------------- one Decoder call (model.py:86-103, modules.py:55-125)
 // rows are (b, qi), qi in [0,nq); query position q0+qi; context ids[b, 0..nkeys-1].
 // Tail: LayerNorm(decoder.norm) + head + (optionally) greedy argmax -> ids_dst[b*32 + dst_off + qi] in one kernel.
+// Caller-supplied pieces of PARSeq.decode (model.py:86-103) that the inference loops never use: explicit query rows,
+// explicit masks, decoder output instead of logits.
+struct DecodeExtras {
+  const float* query = nullptr;          // [B*nq, D] fp32 raw queries (residual base); null -> pos_queries[q0 + qi]
+  const unsigned char* qmask = nullptr;  // [nq, nkeys], 1 = masked
+  const unsigned char* pmask = nullptr;  // [B, nkeys], 1 = masked
+  float* out_norm = nullptr;             // [B*nq, D] fp32: decoder.norm(y) is the result (no head)
+};
 int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int b_first, int B, int nq, int q0, int nkeys,
                 int mode, const int* ids, float* logits_out, long long logits_ld, int* ids_dst, int dst_off,
-                const int* forced, int forced_ld, cudaStream_t st) {
+                const int* forced, int forced_ld, cudaStream_t st, const DecodeExtras* ex = nullptr) {
   const int D = e->D, M = B * nq;
   const std::string Ly = "decoder.layers.0.";
   const float qscale = 1.0f / std::sqrt(static_cast<float>(e->dh_dec));
   const __nv_bfloat16* Wc = e->wb(Ly + "cross_attn.in_proj_weight");
   const float* bc = e->wf(Ly + "cross_attn.in_proj_bias");
   e->cur_cat = CAT_DEC_GEMM;
+  const float* qself = e->qs;            // [L, D] table of W_q LN_q(pos_queries), pre-scaled
+  const unsigned char *qmask = nullptr, *pmask = nullptr;
+  if (ex != nullptr && ex->query != nullptr) {
+    // custom queries: q = scale * (W_q LN_q(query) + b_q), one row per (image, query)
+    PQ_TRY(layernorm(e, ex->query, Ly + "norm_q", 1e-5f, M, sg.yn, nullptr, st));
+    PQ_TRY(gemm(e, sg.yn, D, e->w(Ly + "self_attn.in_proj_weight"), D, e->wf(Ly + "self_attn.in_proj_bias"), M, D, D,
+                pq::EPI_F32, qscale, nullptr, 0, 0, sg.qc, D, st));
+    qself = sg.qc;
+    mode = 2;
+  }
+  if (ex != nullptr && (ex->qmask != nullptr || ex->pmask != nullptr)) {
+    if (mode != 2) {                     // masks with the default queries: expand the table rows (tiny) so mode 2 applies
+      PQ_CUDA(cudaMemcpy2DAsync(sg.qc, static_cast<size_t>(nq) * D * 4, e->qs + static_cast<long long>(q0) * D, 0,
+                                static_cast<size_t>(nq) * D * 4, static_cast<size_t>(B), cudaMemcpyDeviceToDevice, st));
+      qself = sg.qc;
+      mode = 2;
+    }
+    qmask = ex->qmask; pmask = ex->pmask;
+  }
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * nkeys * D);
     const int qsplit = (nq >= 8) ? 4 : 1;
-    PQ_TRY(launch_k(e->lo, pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D < 384 ? D : 384), 0, st, static_cast<const float*>(e->qs),
+    PQ_TRY(launch_k(e->lo, pq::dec_self_attn2_kernel, dim3(B * qsplit), dim3(D < 384 ? D : 384), 0, st, qself,
                     static_cast<const __nv_bfloat16*>(e->kvtab), ids, 32, e->V, D, nq, q0, nkeys, mode, /*eos*/ 0, sg.sa,
-                    qsplit));
+                    qsplit, qmask, pmask));
   }
-  // y = pos_queries[q0+qi] + out_proj(sa): the GEMM stores out_proj(sa) with its TMA epilogue, the LayerNorm kernel
-  // adds the (broadcast) query residual, writes y back and emits norm1(y)
-  const float* posq = e->wf("pos_queries") + static_cast<long long>(q0) * D;
+  // y = query + out_proj(sa): the GEMM stores out_proj(sa) with its TMA epilogue, the LayerNorm kernel adds the query
+  // residual (broadcast pos_queries[q0 + qi], or the caller's rows), writes y back and emits norm1(y)
+  const bool own_q = ex != nullptr && ex->query != nullptr;
+  const float* resid = own_q ? ex->query : e->wf("pos_queries") + static_cast<long long>(q0) * D;
   PQ_TRY(gemm(e, sg.sa, D, e->w(Ly + "self_attn.out_proj.weight"), D, e->wf(Ly + "self_attn.out_proj.bias"), M, D, D,
               pq::EPI_F32, 1.0f, nullptr, 0, 0, sg.y, D, st));
-  PQ_TRY(layernorm(e, sg.y, Ly + "norm1", 1e-5f, M, sg.yn, nullptr, st, posq, nq, sg.y));
+  PQ_TRY(layernorm(e, sg.y, Ly + "norm1", 1e-5f, M, sg.yn, nullptr, st, resid, own_q ? M : nq, sg.y));
   PQ_TRY(gemm(e, sg.yn, D, Wc, D, bc, M, D, D, pq::EPI_F32, qscale, nullptr, 0, 0, sg.qc, D, st));
   {
     TimedScope ts(e, st, CAT_DEC_ATTN, 4.0 * M * e->T * D);
@@ -715,7 +743,10 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int b_first, int B, 
               1.0f, nullptr, 0, 0, sg.hd, e->Md, st));
   PQ_TRY(gemm(e, sg.hd, e->Md, e->w(Ly + "linear2.weight"), e->Md, e->wf(Ly + "linear2.bias"), M, D, e->Md, pq::EPI_F32,
               1.0f, sg.y, D, 0, sg.y, D, st));
-  if (nq > 1 && ids_dst == nullptr) {
+  if (ex != nullptr && ex->out_norm != nullptr) {
+    // PARSeq.decode returns the decoder output: final LayerNorm only (modules.py:123-125)
+    PQ_TRY(layernorm(e, sg.y, "decoder.norm", 1e-5f, M, sg.yn, ex->out_norm, st));
+  } else if (nq > 1 && ids_dst == nullptr) {
     // multi-query passes (refine / NAR): LayerNorm kernel + tcgen05 GEMM for the head (weights read once per tile).
     // Chosen by pass type, not by batch size, so that a row's result does not depend on the batch it is computed in.
     PQ_TRY(layernorm(e, sg.y, "decoder.norm", 1e-5f, M, sg.yn, nullptr, st));
@@ -1411,6 +1442,92 @@ int parseq_encode(parseq_engine* e, int32_t batch, const float* images, float* m
   }
   PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
   PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return PARSEQ_OK;
+}
+
+int parseq_decode(parseq_engine* e, int32_t batch, int32_t ctx_len, int32_t num_queries, const int32_t* tgt, const float* memory,
+                  const float* query, const uint8_t* query_mask, const uint8_t* padding_mask, float* out,
+                  parseq_stream_t stream) {
+  if (e == nullptr || tgt == nullptr || memory == nullptr || out == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken) return fail(PARSEQ_ERR_STATE, "engine workspace is gone (a failed resize): destroy the handle");
+  if (!e->finalized) return fail(PARSEQ_ERR_STATE, "parseq_finalize has not been called");
+  if (e->arch != 0) return fail(PARSEQ_ERR_UNSUPPORTED, "decode: PARSeq only");
+  if (batch < 0 || ctx_len < 1 || ctx_len > e->L || num_queries < 1 || num_queries > e->L)
+    return fail(PARSEQ_ERR_INVALID_ARG, "decode: 1 <= context length, queries <= max_label_length + 1");
+  if (batch == 0) return PARSEQ_OK;
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  PQ_CUDA(cudaEventRecord(e->ev_in, user));
+  PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
+  const int D = e->D, T = e->T, J = ctx_len, NQ = num_queries;
+  const std::string Ly = "decoder.layers.0.";
+  const __nv_bfloat16* Wkv = e->wb(Ly + "cross_attn.in_proj_weight") + static_cast<long long>(D) * D;
+  const float* bkv = e->wf(Ly + "cross_attn.in_proj_bias") + D;
+  parseq_engine::Stage& sg = e->stages[0];
+  cudaStream_t st = e->main;
+  for (int b0 = 0; b0 < batch; b0 += e->dec_chunk) {
+    const int Bc = (batch - b0 < e->dec_chunk) ? (batch - b0) : e->dec_chunk;
+    // memory (fp32, caller's) -> bf16 operand -> cross K/V cache rows [0, Bc * T)
+    const long long n4 = 1ll * Bc * T * D / 4;
+    pq::f32_to_bf16_kernel<<<static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 8)), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(memory + 1ll * b0 * T * D), reinterpret_cast<uint2*>(e->mem), n4);
+    PQ_CUDA(cudaGetLastError());
+    e->cur_cat = CAT_DEC_GEMM;
+    PQ_TRY(gemm(e, e->mem, D, Wkv, D, bkv, Bc * T, 2 * D, D, pq::EPI_BF16, 1.0f, nullptr, 0, 0, e->ckv, 2 * D, st,
+                1ll * e->max_batch * T));
+    pq::copy_ids_kernel<<<(Bc * 32 + 255) / 256, 256, 0, st>>>(tgt + 1ll * b0 * J, J, sg.ids_ctx, Bc);
+    PQ_CUDA(cudaGetLastError());
+    e->launches += 2;
+    DecodeExtras ex;
+    ex.query = query ? query + 1ll * b0 * NQ * D : nullptr;
+    ex.qmask = query_mask;
+    ex.pmask = padding_mask ? padding_mask + 1ll * b0 * J : nullptr;
+    ex.out_norm = out + 1ll * b0 * NQ * D;
+    PQ_TRY(decode_pass(e, sg, 0, Bc, NQ, 0, J, 0, sg.ids_ctx, nullptr, 0, nullptr, 0, nullptr, 0, st, &ex));
+  }
+  PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
+  PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return PARSEQ_OK;
+}
+
+int parseq_head(parseq_engine* e, int32_t rows, const float* x, float* logits, parseq_stream_t stream) {
+  if (e == nullptr || x == nullptr || logits == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->broken || !e->finalized) return fail(PARSEQ_ERR_STATE, "engine not ready");
+  if (rows <= 0) return rows == 0 ? PARSEQ_OK : fail(PARSEQ_ERR_INVALID_ARG, "negative rows");
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  PQ_CUDA(cudaEventRecord(e->ev_in, user));
+  PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_in, 0));
+  const int D = e->D;
+  const int cap = e->dec_chunk * e->L;                 // rows of the bf16 staging buffer of a decoder chain
+  parseq_engine::Stage& sg = e->stages[0];
+  for (int r0 = 0; r0 < rows; r0 += cap) {
+    const int n = (rows - r0 < cap) ? (rows - r0) : cap;
+    const long long n4 = 1ll * n * D / 4;
+    pq::f32_to_bf16_kernel<<<static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 8)), 256, 0, e->main>>>(
+        reinterpret_cast<const float4*>(x + 1ll * r0 * D), reinterpret_cast<uint2*>(sg.yn), n4);
+    PQ_CUDA(cudaGetLastError());
+    e->launches++;
+    e->cur_cat = CAT_DEC_GEMM;
+    PQ_TRY(gemm(e, sg.yn, D, e->w("head.weight"), D, e->wf("head.bias"), n, e->C, D, pq::EPI_F32, 1.0f, nullptr, 0, 0,
+                logits + 1ll * r0 * e->C, e->C, e->main));
+  }
+  PQ_CUDA(cudaEventRecord(e->ev_out, e->main));
+  PQ_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return PARSEQ_OK;
+}
+
+int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* out, parseq_stream_t stream) {
+  if (e == nullptr || ids == nullptr || out == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null argument");
+  if (e->arch != 0) return fail(PARSEQ_ERR_UNSUPPORTED, "text_embed: PARSeq only");
+  if (n <= 0) return n == 0 ? PARSEQ_OK : fail(PARSEQ_ERR_INVALID_ARG, "negative count");
+  if (!e->slots[e->index.at("text_embed.embedding.weight")].set) return fail(PARSEQ_ERR_STATE, "weights not set");
+  PQ_CUDA(cudaSetDevice(e->cfg.device));
+  const long long total = 1ll * n * e->D;
+  pq::text_embed_kernel<<<static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148ll * 8)), 256, 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(ids, e->wf("text_embed.embedding.weight"), out, n, e->D, e->V,
+                                                                    std::sqrt(static_cast<float>(e->D)));
+  PQ_CUDA(cudaGetLastError());
   return PARSEQ_OK;
 }
 

@@ -479,9 +479,14 @@ __global__ void set_int_kernel(int* p, int v) {
 //            all-False);  mode 1 (cloze refine): key k masked iff k == q+1 or an EOS occurs in ids[b, 0..k]
 //            (model.py:157,163)
 // out bf16 [B*nq, D] (A operand of the out-projection GEMM).
+//            mode 2 (PARSeq.decode with caller-supplied masks, model.py:86-103): Qs holds one query row per (image,
+//            query) [B*nq, D]; key k of query qi is masked iff qmask[qi*nkeys + k] or pmask[b*nkeys + k] (either may be
+//            null); a row with every key masked yields NaN, as torch's softmax over -inf does
 __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_bfloat16* __restrict__ kvtab,
                                       const int* __restrict__ ids, int ids_ld, int V, int D, int nq, int q0, int nkeys,
-                                      int mode, int eos_id, __nv_bfloat16* __restrict__ out, int qsplit) {
+                                      int mode, int eos_id, __nv_bfloat16* __restrict__ out, int qsplit,
+                                      const unsigned char* __restrict__ qmask = nullptr,
+                                      const unsigned char* __restrict__ pmask = nullptr) {
   // grid = B * qsplit: CTA (b, part) handles queries [part*nq/qsplit, (part+1)*nq/qsplit) of image b
   __shared__ int s_ids[32];
   __shared__ int s_first_eos;
@@ -523,11 +528,16 @@ __global__ void dec_self_attn2_kernel(const float* __restrict__ Qs, const __nv_b
     vreg[k] = (k < nkeys) ? __bfloat162float(kvtab[(static_cast<long long>(k) * V + s_ids[k]) * 2 * D + D + h * 32 + lane]) : 0.f;
   for (int qi = q_begin; qi < q_end; ++qi) {
     const int qpos = q0 + qi;
-    const float qv = __ldg(Qs + static_cast<long long>(qpos) * D + h * 32 + lane);   // lane j holds q_j
+    const long long qrow = (mode == 2) ? (static_cast<long long>(b) * nq + qi) : qpos;
+    const float qv = __ldg(Qs + qrow * D + h * 32 + lane);   // lane j holds q_j
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) s = fmaf(__shfl_sync(0xffffffffu, qv, j), kreg[j], s);
-    const bool masked = (lane >= nkeys) || ((mode == 1) && (lane == qpos + 1 || lane >= first_eos));
+    bool masked = (lane >= nkeys) || ((mode == 1) && (lane == qpos + 1 || lane >= first_eos));
+    if (mode == 2 && lane < nkeys) {
+      if (qmask != nullptr && qmask[qi * nkeys + lane] != 0) masked = true;
+      if (pmask != nullptr && pmask[static_cast<long long>(b) * nkeys + lane] != 0) masked = true;
+    }
     if (masked) s = -INFINITY;
     float mx = s;
 #pragma unroll
@@ -868,6 +878,31 @@ __global__ void postprocess_kernel(const float* __restrict__ logits, int B, int 
   if (lane == 0) {
     lengths[b] = len;
     confidence[b] = conf;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary helpers of the module API (PARSeq.decode / head / text_embed called on their own).
+__global__ void f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+// ids [B, J] (row pitch J) -> context buffer [B, 32]
+__global__ void copy_ids_kernel(const int* __restrict__ src, int J, int* __restrict__ dst, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 32) dst[i] = ((i & 31) < J) ? src[(i >> 5) * J + (i & 31)] : 0;
+}
+// TokenEmbedding.forward (modules.py:175-176): out[i, :] = sqrt(D) * E[ids[i], :]
+__global__ void text_embed_kernel(const int* __restrict__ ids, const float* __restrict__ E, float* __restrict__ out, int n,
+                                  int D, int V, float scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(n) * D;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int tok = ids[i / D];
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    out[i] = scale * E[static_cast<long long>(tok) * D + (i % D)];
   }
 }
 

@@ -58,6 +58,35 @@ class _Holder(nn.Module):
     """Parameter container; nested so that state_dict keys equal the reference's."""
 
 
+class _HeadModule(_Holder):
+    """`model.head` (model.py:63, nn.Linear(embed_dim, num_tokens - 2)) as a callable: x [..., D] fp32 -> logits."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        owner = self.__dict__["_owner"]()
+        eng = owner.engine()
+        D = owner.cfg.embed_dim
+        if x.device.type != "cuda":
+            raise RuntimeError("head() takes CUDA tensors (no CPU fallback)")
+        x2 = x.to(torch.float32).reshape(-1, D).contiguous()
+        out = torch.empty((x2.shape[0], owner.cfg.num_classes), dtype=torch.float32, device=x.device)
+        eng.head(x2.shape[0], x2.data_ptr(), out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+        return out.reshape(*x.shape[:-1], owner.cfg.num_classes)
+
+
+class _TextEmbedModule(_Holder):
+    """`model.text_embed` (modules.py:168-176, TokenEmbedding) as a callable: ids [...] -> sqrt(D) * embedding[ids]."""
+
+    def forward(self, tokens: Tensor) -> Tensor:
+        owner = self.__dict__["_owner"]()
+        eng = owner.engine()
+        if tokens.device.type != "cuda":
+            raise RuntimeError("text_embed() takes CUDA tensors (no CPU fallback)")
+        ids = tokens.to(torch.int32).contiguous()
+        out = torch.empty((*ids.shape, owner.cfg.embed_dim), dtype=torch.float32, device=ids.device)
+        eng.text_embed(ids.numel(), ids.data_ptr(), out.data_ptr(), torch.cuda.current_stream(ids.device).cuda_stream)
+        return out
+
+
 def _register(root: nn.Module, key: str, tensor: Tensor):
     parts = key.split(".")
     mod = root
@@ -82,6 +111,13 @@ class _EngineModule(nn.Module):
         self._engine: Optional[Engine] = None
         self._engine_sig = None
         self._options = {}
+        # `head` / `text_embed` are callable like the reference's submodules (they hold the same parameters)
+        import weakref
+        for name, cls in (("head", _HeadModule), ("text_embed", _TextEmbedModule)):
+            if hasattr(self, name):
+                mod = getattr(self, name)
+                mod.__class__ = cls
+                mod.__dict__["_owner"] = weakref.ref(self)
 
     # ---- engine plumbing -------------------------------------------------------------------
     @property
@@ -169,9 +205,51 @@ class ParseqModel(_EngineModule):
     def encode(self, img: Tensor) -> Tensor:
         return self._features(img)
 
-    def decode(self, *args, **kwargs):
-        raise NotImplementedError("arbitrary-mask decode() is a training-time API (system.py:169-200) and is not "
-                                  "part of the inference engine")
+    @staticmethod
+    def _bool_mask(mask: Optional[Tensor], shape, dev) -> Optional[Tensor]:
+        """torch's attention masks are bool (True = masked) or additive floats (-inf = masked, 0 = keep)."""
+        if mask is None:
+            return None
+        if mask.dtype == torch.bool:
+            m = mask
+        elif mask.is_floating_point():
+            if bool(((mask != 0) & ~torch.isneginf(mask)).any()):
+                raise NotImplementedError("additive attention masks other than 0 / -inf are not supported by the engine")
+            m = torch.isneginf(mask)
+        else:
+            m = mask != 0
+        if tuple(m.shape) != tuple(shape):
+            raise AssertionError(f"mask shape {tuple(m.shape)} != {tuple(shape)}")
+        return m.to(device=dev, dtype=torch.uint8).contiguous()
+
+    def decode(self, tgt: Tensor, memory: Tensor, tgt_mask: Optional[Tensor] = None,
+               tgt_padding_mask: Optional[Tensor] = None, tgt_query: Optional[Tensor] = None,
+               tgt_query_mask: Optional[Tensor] = None) -> Tensor:
+        """model.py:86-103: decoder output [N, NQ, D] (before `head`) for context ids `tgt` [N, J] and encoder `memory`
+        [N, T, D].  `tgt_mask` acts on the content stream only, which the depth-1 decoder never updates
+        (modules.py:117-123), so it is accepted and ignored."""
+        eng = self.engine()
+        dev = memory.device
+        if dev.type != "cuda" or tgt.device != dev:
+            raise RuntimeError("decode() takes CUDA tensors (no CPU fallback)")
+        N, J = tgt.shape
+        D, T = self.cfg.embed_dim, self.cfg.enc_tokens
+        if tuple(memory.shape) != (N, T, D):
+            raise AssertionError(f"memory shape {tuple(memory.shape)} != {(N, T, D)}")
+        ids = tgt.to(torch.int32).contiguous()
+        mem = memory.to(torch.float32).contiguous()
+        q = None
+        NQ = J
+        if tgt_query is not None:
+            NQ = tgt_query.shape[1]
+            q = tgt_query.to(device=dev, dtype=torch.float32).expand(N, NQ, D).contiguous()
+        qm = self._bool_mask(tgt_query_mask, (NQ, J), dev)
+        pm = self._bool_mask(tgt_padding_mask, (N, J), dev)
+        out = torch.empty((N, NQ, D), dtype=torch.float32, device=dev)
+        eng.decode(N, J, NQ, ids.data_ptr(), mem.data_ptr(), q.data_ptr() if q is not None else None,
+                   qm.data_ptr() if qm is not None else None, pm.data_ptr() if pm is not None else None, out.data_ptr(),
+                   torch.cuda.current_stream(dev).cuda_stream)
+        return out
 
     def forward(self, tokenizer: Tokenizer, images: Tensor, max_length: Optional[int] = None,
                 return_ids: bool = False, forced_ids: Optional[Tensor] = None,
