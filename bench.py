@@ -240,24 +240,30 @@ def build_model(experiment, dev, decode_ar, refine_iters, opts=None, seed=0):
     return cfg, sd, m.eval().to(dev)
 
 
+def infer(fn, x):
+    import torch
+    with torch.inference_mode():
+        return fn(x)
+
+
 def other_configs(dev, world, peak_tf, dist):
     """BASELINE.json configs[0], [3], [4]: device-timed, module API (`model(x)`), same engine."""
     import torch
     from parseq_b200.weights import synth_images
     out = {}
-    with torch.inference_mode():
+    if True:
         if world == 1:
             # C1: PARSeq-Ti bs=1 NAR (decode_ar=False, refine_iters=0): latency
             cfg, _, m = build_model("parseq-tiny", dev, False, 0)
             x = synth_images(cfg, 1, 3).to(dev)
-            ms = device_time_ms(lambda: m(x), 300, 20)
+            ms = device_time_ms(lambda: infer(m, x), 300, 20)
             out["C1"] = {"workload": "PARSeq-Ti 32x128 bs=1 NAR, no refine (configs[0])", "ms": ms, "images_per_s": 1000.0 / ms,
                          "frac_of_tensor_peak": (1000.0 / ms) * ALG_GFLOP_C1 * 1e9 / (peak_tf * 1e12)}
             del m
             # C4: PARSeq-S bs=1024 AR + 3 refine (two super-chunks of 512)
             cfg, _, m = build_model("parseq", dev, True, 3)
             x = synth_images(cfg, 1024, 4).to(dev)
-            ms = device_time_ms(lambda: m(x), 5, 2)
+            ms = device_time_ms(lambda: infer(m, x), 5, 2)
             ips = 1024 * 1000.0 / ms
             out["C4"] = {"workload": "PARSeq-S 32x128 bs=1024 AR + 3 refine, 1 GPU (configs[3])", "ms": ms, "images_per_s": ips,
                          "frac_of_tensor_peak": ips * ALG_GFLOP_C4 * 1e9 / (peak_tf * 1e12)}
@@ -265,8 +271,8 @@ def other_configs(dev, world, peak_tf, dist):
         # C5: ViT-B-width encoder 48x160 (T = 240, D = 768), 256 images per GPU (bs=2048 over 8 GPUs)
         cfg, _, m = build_model("parseq-base-48x160", dev, True, 1, {"max_batch": 256})
         x = synth_images(cfg, 256, 5).to(dev)
-        ms_full = device_time_ms(lambda: m(x), 4, 2)
-        ms_enc = device_time_ms(lambda: m.model.encode(x), 4, 2)
+        ms_full = device_time_ms(lambda: infer(m, x), 4, 2)
+        ms_enc = device_time_ms(lambda: infer(m.model.encode, x), 4, 2)
         if dist is not None:
             t = torch.tensor([ms_full, ms_enc], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

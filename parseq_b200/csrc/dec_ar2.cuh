@@ -230,7 +230,12 @@ struct A2Ring {
 template <int NTW>
 __device__ __forceinline__ void mma_box(float (&acc)[NTW][4], const uint8_t* atile, int mi, const uint8_t* box, int nt0,
                                         int lane, int ksteps = 4) {
+  // Every n8 tile accumulates its even and odd k-steps in separate registers (two independent dependency chains per
+  // box: the phases are latency-, not throughput-bound); the odd chain is folded into `acc` before returning.
   const uint32_t abase = smem_u32(atile), bbase = smem_u32(box);
+  float odd[NTW][4];
+#pragma unroll
+  for (int j = 0; j < NTW; ++j) odd[j][0] = odd[j][1] = odd[j][2] = odd[j][3] = 0.f;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     if (ks < ksteps) {
@@ -241,10 +246,19 @@ __device__ __forceinline__ void mma_box(float (&acc)[NTW][4], const uint8_t* ati
         const int n = (nt0 + np * 2) * 8 + (lane & 7) + (lane >> 4) * 8;
         uint32_t b0, b1, b2, b3;
         ldmatrix_x4(bbase + box_off(n, ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(acc[np * 2], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(acc[np * 2 + 1], a0, a1, a2, a3, b2, b3);
+        if (ks & 1) {
+          mma_bf16_16816(odd[np * 2], a0, a1, a2, a3, b0, b1);
+          mma_bf16_16816(odd[np * 2 + 1], a0, a1, a2, a3, b2, b3);
+        } else {
+          mma_bf16_16816(acc[np * 2], a0, a1, a2, a3, b0, b1);
+          mma_bf16_16816(acc[np * 2 + 1], a0, a1, a2, a3, b2, b3);
+        }
       }
     }
+  }
+#pragma unroll
+  for (int j = 0; j < NTW; ++j) {
+    acc[j][0] += odd[j][0]; acc[j][1] += odd[j][1]; acc[j][2] += odd[j][2]; acc[j][3] += odd[j][3];
   }
 }
 
@@ -497,13 +511,17 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       for (int oi = 0; oi < n_own; ++oi) {
         const int r = rank + A2_CS * oi;
         const float* qrow = s_q + oi * D;
-        float sacc[MH][2][2][4];                      // [m tile][key block][n8 tile][frag]
+        float sacc[MH][2][2][4];                      // [m tile][key block][n8 tile][frag]; q_hi term
+        float slo[MH][2][2][4];                       // q_lo term: its own dependency chain, added before the softmax
 #pragma unroll
         for (int a = 0; a < MH; ++a)
 #pragma unroll
           for (int b = 0; b < 2; ++b)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) sacc[a][b][c][0] = sacc[a][b][c][1] = sacc[a][b][c][2] = sacc[a][b][c][3] = 0.f;
+            for (int c = 0; c < 2; ++c) {
+              sacc[a][b][c][0] = sacc[a][b][c][1] = sacc[a][b][c][2] = sacc[a][b][c][3] = 0.f;
+              slo[a][b][c][0] = slo[a][b][c][1] = slo[a][b][c][2] = slo[a][b][c][3] = 0.f;
+            }
         // ---- S = Q_blockdiag K^T: K box kb holds dims [64 kb, 64 kb + 64) = heads 2 kb, 2 kb + 1 ----
         for (int kb = 0; kb < KT; ++kb) {
 #pragma unroll
@@ -533,10 +551,10 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
                 for (int a = 0; a < MH; ++a) {
                   if (a == mh) {
                     mma_bf16_16816(sacc[a][tbi][0], ah0, ah1, ah2, ah3, b0, b1);
-                    mma_bf16_16816(sacc[a][tbi][0], al0, al1, al2, al3, b0, b1);
+                    mma_bf16_16816(slo[a][tbi][0], al0, al1, al2, al3, b0, b1);
                     if (ntk == 2) {
                       mma_bf16_16816(sacc[a][tbi][1], ah0, ah1, ah2, ah3, b2, b3);
-                      mma_bf16_16816(sacc[a][tbi][1], al0, al1, al2, al3, b2, b3);
+                      mma_bf16_16816(slo[a][tbi][1], al0, al1, al2, al3, b2, b3);
                     }
                   }
                 }
@@ -549,6 +567,12 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
         float rmax[MH][2];
 #pragma unroll
         for (int a = 0; a < MH; ++a) {
+#pragma unroll
+          for (int tbi = 0; tbi < 2; ++tbi)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int f = 0; f < 4; ++f) sacc[a][tbi][c][f] += slo[a][tbi][c][f];
           rmax[a][0] = rmax[a][1] = -INFINITY;
 #pragma unroll
           for (int tbi = 0; tbi < 2; ++tbi)
@@ -617,7 +641,8 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
         __syncthreads();
         // ---- O = P V: V box kb holds dims [64 kb, +64); warp w -> dims 8 w .. 8 w + 7 of the box, head 2 kb + w / 4 ----
         for (int kb = 0; kb < KT; ++kb) {
-          float oacc[4] = {0.f, 0.f, 0.f, 0.f};
+          float oacc[4] = {0.f, 0.f, 0.f, 0.f}, oacc1[4] = {0.f, 0.f, 0.f, 0.f}, oacc2[4] = {0.f, 0.f, 0.f, 0.f},
+                oacc3[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains: (P_hi, P_lo) x (even, odd k16 step)
           const int hh = 2 * kb + (warp >> 2);
           const int mh = hh >> 4, hrow = hh & 15;
 #pragma unroll
@@ -638,13 +663,20 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
                   ldmatrix_x4(po + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + (lane >> 4) * 8), a0, a1, a2, a3);
                   ldmatrix_x4(po + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + 16 + (lane >> 4) * 8), c0, c1, c2,
                               c3);
-                  mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);
-                  mma_bf16_16816(oacc, c0, c1, c2, c3, v2, v3);
+                  if (hl == 0) {
+                    mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);
+                    mma_bf16_16816(oacc1, c0, c1, c2, c3, v2, v3);
+                  } else {
+                    mma_bf16_16816(oacc2, a0, a1, a2, a3, v0, v1);
+                    mma_bf16_16816(oacc3, c0, c1, c2, c3, v2, v3);
+                  }
                 }
               }
               ring.release();
             }
           }
+#pragma unroll
+          for (int f = 0; f < 4; ++f) oacc[f] = (oacc[f] + oacc1[f]) + (oacc2[f] + oacc3[f]);
           // the head's row of the 16 x 8 accumulator: (g == hrow) -> c0, c1; (g + 8 == hrow) -> c2, c3
           float tot = 0.f;
 #pragma unroll

@@ -702,8 +702,10 @@ int decode_pass(parseq_engine* e, parseq_engine::Stage& sg, int b_first, int B, 
   }
   if (ex != nullptr && (ex->qmask != nullptr || ex->pmask != nullptr)) {
     if (mode != 2) {                     // masks with the default queries: expand the table rows (tiny) so mode 2 applies
-      PQ_CUDA(cudaMemcpy2DAsync(sg.qc, static_cast<size_t>(nq) * D * 4, e->qs + static_cast<long long>(q0) * D, 0,
-                                static_cast<size_t>(nq) * D * 4, static_cast<size_t>(B), cudaMemcpyDeviceToDevice, st));
+      const int n4 = nq * D / 4;
+      PQ_TRY(launch_k(e->lo, pq::bcast_rows_kernel, dim3(static_cast<unsigned>(std::min((B * n4 + 255) / 256, 148 * 8))), dim3(256), 0, st,
+                      reinterpret_cast<const float4*>(e->qs + static_cast<long long>(q0) * D), reinterpret_cast<float4*>(sg.qc), n4, B));
+      e->launches++;
       qself = sg.qc;
       mode = 2;
     }

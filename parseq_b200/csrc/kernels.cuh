@@ -890,6 +890,12 @@ __global__ void f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restri
     y[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
 }
+// dst[b, :] = src[:] for b < B (n floats, n % 4 == 0)
+__global__ void bcast_rows_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int n4, int B) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < static_cast<long long>(B) * n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[i % n4];
+}
 // ids [B, J] (row pitch J) -> context buffer [B, 32]
 __global__ void copy_ids_kernel(const int* __restrict__ src, int J, int* __restrict__ dst, int B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -125,7 +125,24 @@ class _EngineModule(nn.Module):
         return next(self.parameters()).device
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Cheap staleness check of the engine's weight copy: version counters of every parameter (in-place updates,
+        load_state_dict) + the storage addresses of the first / last one (`.to()` moves).  The parameter list is cached:
+        walking the module tree costs more than a bs=1 forward's launch overhead."""
+        pl = self.__dict__.get("_plist")
+        if pl is None:
+            pl = list(self.parameters())
+            self.__dict__["_plist"] = pl
+        try:
+            vers = tuple(p._version for p in pl)
+        except RuntimeError:           # inference tensors carry no version counter
+            vers = tuple(id(p) for p in pl)
+        return (vers, pl[0].data_ptr(), pl[-1].data_ptr(), len(pl))
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.__dict__.pop("_plist", None)
+        self._engine_sig = None
+        return out
 
     def engine(self) -> Engine:
         dev = self._device

