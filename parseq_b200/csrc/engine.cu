@@ -401,6 +401,7 @@ struct parseq_engine {
   pq::DecAr2Maps ar2_maps;          // TMA descriptors of the decoder weights (built by parseq_finalize) and the K/V cache
   bool ar2_maps_ok = false;
   int ar2_clusters[3] = {0, 0, 0};  // max co-resident clusters of the MT = 1 / 2 instantiation (index = MT)
+  int ar_clusters_override = 0;     // option "ar_clusters": clusters the AR kernel spreads a batch over (0 = derived)
   int fuse_ln = 3;                  // bit 0: attn.proj, bit 1: mlp.fc2 also produce the LayerNorm that follows (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
   float *ar_y = nullptr, *ar_qc = nullptr, *ar_part = nullptr;
@@ -872,8 +873,15 @@ int ar2_max_clusters(parseq_engine* e) {
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, pq::dec_ar2_kernel<D, MT>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
-    n = e->lo.sm_count / (2 * pq::A2_CS);       // conservative: two clusters of 8 per GPC pair
+    n = e->lo.sm_count / pq::A2_CS;
   }
+  // A cluster lives inside one GPC.  B200: 8 GPCs of 16 / 18 / 20 SMs -> two 8-CTA clusters each = 16 co-resident
+  // clusters, although the occupancy query answers floor(148 / 8) = 18: with 18 clusters launched the last two ran as a
+  // second wave and the kernel took twice as long (measured, bench r2d: 3.7 ms vs 1.9 ms).  Cap at 2 per GPC
+  // (GPC count estimated from the SM count; option "ar_clusters" overrides).
+  const int gpcs = (e->lo.sm_count + 9) / 18;
+  if (n > 2 * gpcs) n = 2 * gpcs;
+  if (e->ar_clusters_override > 0) n = e->ar_clusters_override;
   e->ar2_clusters[MT] = n;
   return n;
 }
@@ -1573,6 +1581,13 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   }
   if (n == "use_graph") { e->use_graph = value != 0; return PARSEQ_OK; }
   if (n == "ar_prof") { e->ar_prof_on = value != 0; drop_graphs(e); return PARSEQ_OK; }
+  if (n == "ar_clusters") {
+    if (value < 0 || value > 1024) return fail(PARSEQ_ERR_INVALID_ARG, "ar_clusters out of range");
+    e->ar_clusters_override = static_cast<int>(value);
+    e->ar2_clusters[1] = e->ar2_clusters[2] = 0;
+    drop_graphs(e);
+    return PARSEQ_OK;
+  }
   if (n == "ar_kernel") {           // 0: AR loop as separate kernels, 1: grid-barrier kernel (dec_ar.cuh), 2: cluster kernel
     if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "ar_kernel: 0 / 1 / 2");
     e->use_ar_kernel = value != 0;
