@@ -137,6 +137,8 @@ int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* ou
 
 /* Introspection used by bench.py / tests. */
 int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count of kernels launched */
+/* Debug counters by name ("ar2_occupancy_mt2", "ar2_clusters_mt2", "ar_last_per", "ar_last_clusters", "sm_count"); -1 if unknown. */
+int64_t parseq_debug_int(parseq_engine* e, const char* name);
 /* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per encoder pass inside a
  * super-chunk), "dec_chunk" (images per decoder chain; the chains of a super-chunk run concurrently on their own
  * streams), "use_graph" (0/1), "pdl" (programmatic dependent launch, 0/1), "timing" (1: record a CUDA-event pair around every launch

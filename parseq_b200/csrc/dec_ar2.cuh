@@ -6,9 +6,9 @@
 //
 // Work split inside a cluster (rank k of 8, rows = images of the cluster, D = embed dim, DS = D/8):
 //   * every projection is split over N: CTA k computes output columns [k*DS, (k+1)*DS) for ALL rows on mma.sync
-//     tiles; the weight slice streams through a ring of 16 KB shared-memory slots filled by TMA (128B-swizzled boxes;
-//     full / empty mbarriers per slot, the issuing thread rotates over the warps, no CTA-wide barrier per box): each
-//     weight byte is read from L2 once per cluster and step;
+//     tiles; the weight slice streams through a ring of 16 KB shared-memory slots filled by TMA (128B-swizzled boxes,
+//     one elected thread issues the next box whenever a slot is released): each weight byte is read from L2 once per
+//     cluster and step;
 //   * attention is split over images: CTA k owns rows k, k+8, ... ; cross-attention streams the image's K/V cache
 //     (T x 2D bf16) through the same ring and runs QK^T / PV as block-diagonal tensor-core products
 //     (rows = heads; q and P are split into bf16 hi + lo terms, i.e. ~16 mantissa bits);
@@ -137,8 +137,7 @@ template <int D, int MT>
 struct A2Ring {
   using Cfg = A2Cfg<D, MT>;
   uint8_t* slots;
-  uint64_t* full;                      // [NSLOT] TMA -> consumers (transaction bytes)
-  uint64_t* empty;                     // [NSLOT] consumers -> issuing thread (one arrival per warp)
+  uint64_t* full;
   const DecAr2Maps* maps;
   int rank, n_own, img0, per_here;     // img0: first image of the cluster
   int tbox, tb, T;
@@ -148,7 +147,7 @@ struct A2Ring {
 
   __device__ void init(uint8_t* slots_, uint64_t* full_, const DecAr2Maps* maps_, int rank_, int n_own_, int img0_, int tbox_,
                        int tb_, int T_, int steps) {
-    slots = slots_; full = full_; empty = full_ + Cfg::NSLOT; maps = maps_; rank = rank_; n_own = n_own_; img0 = img0_; tbox = tbox_; tb = tb_; T = T_;
+    slots = slots_; full = full_; maps = maps_; rank = rank_; n_own = n_own_; img0 = img0_; tbox = tbox_; tb = tb_; T = T_;
     seg_b = Cfg::NSL_S;
     seg_c = 2 * Cfg::NSL_S;
     seg_d = seg_c + n_own * 2 * Cfg::KT * tb;
@@ -216,22 +215,10 @@ struct A2Ring {
     mbar_wait(&full[s], static_cast<uint32_t>((cons / Cfg::NSLOT) & 1));
     return slots + s * A2_SLOT;
   }
-  // All threads.  No CTA-wide barrier per item: every warp signals that it is done with the slot; the warp whose turn
-  // it is to issue (rotating, so that the serial TMA-issue cost and the wait for the slowest warp are shared) refills
-  // it as soon as all eight have; the other warps run ahead into the next items as far as their data has arrived.
-  __device__ __forceinline__ void release() {
-    const int s = cons % Cfg::NSLOT;
-    const uint32_t par = static_cast<uint32_t>((cons / Cfg::NSLOT) & 1);
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+  __device__ __forceinline__ void release() {                  // all threads; the slot just consumed is refilled
+    __syncthreads();
     ++cons;
-    if (prod < total && (threadIdx.x >> 5) == (prod & 7)) {
-      if ((threadIdx.x & 31) == 0) {
-        mbar_wait(&empty[s], par);           // every warp has finished reading the item that occupied this slot
-        issue(prod_it, prod_slot);           // prod_slot == s
-      }
-      __syncwarp();
-    }
+    if (prod < total && threadIdx.x == ((prod & 7) << 5)) issue(prod_it, prod_slot);
     ++prod;
     if (++prod_it == items_per_step) prod_it = 0;
     if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
@@ -311,7 +298,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
 
   grid_dep_launch();
   if (tid == 0) {
-    for (int s = 0; s < Cfg::NSLOT; ++s) { mbar_init(&s_bar[s], 1); mbar_init(&s_bar[Cfg::NSLOT + s], A2_THREADS / 32); }
+    for (int s = 0; s < Cfg::NSLOT; ++s) mbar_init(&s_bar[s], 1);
     fence_mbar_init();
     prefetch_tmap(&maps.wo_s); prefetch_tmap(&maps.wq_c); prefetch_tmap(&maps.wo_c); prefetch_tmap(&maps.w1);
     prefetch_tmap(&maps.w2); prefetch_tmap(&maps.wh); prefetch_tmap(&maps.ckv);

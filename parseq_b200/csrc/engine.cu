@@ -401,6 +401,8 @@ struct parseq_engine {
   pq::DecAr2Maps ar2_maps;          // TMA descriptors of the decoder weights (built by parseq_finalize) and the K/V cache
   bool ar2_maps_ok = false;
   int ar2_clusters[3] = {0, 0, 0};  // max co-resident clusters of the MT = 1 / 2 instantiation (index = MT)
+  int ar2_occ[3] = {0, 0, 0};       // what cudaOccupancyMaxActiveClusters answered (debug)
+  int ar_last_per = 0, ar_last_ncl = 0;
   int ar_clusters_override = 0;     // option "ar_clusters": clusters the AR kernel spreads a batch over (0 = derived)
   int fuse_ln = 3;                  // bit 0: attn.proj, bit 1: mlp.fc2 also produce the LayerNorm that follows (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
@@ -875,6 +877,7 @@ int ar2_max_clusters(parseq_engine* e) {
     cudaGetLastError();
     n = e->lo.sm_count / pq::A2_CS;
   }
+  e->ar2_occ[MT] = n;
   // A cluster lives inside one GPC.  B200: 8 GPCs of 16 / 18 / 20 SMs -> two 8-CTA clusters each = 16 co-resident
   // clusters, although the occupancy query answers floor(148 / 8) = 18: with 18 clusters launched the last two ran as a
   // second wave and the kernel took twice as long (measured, bench r2d: 3.7 ms vs 1.9 ms).  Cap at 2 per GPC
@@ -894,6 +897,7 @@ int ar2_dispatch(parseq_engine* e, pq::DecAr2Params& p, cudaStream_t st) {
   if (per <= 16 || !kHas2) {
     if (per > 16) per = 16;
     p.per = per;
+    e->ar_last_per = per; e->ar_last_ncl = (p.B + per - 1) / per;
     return ar2_launch<D, 1>(e, p, (p.B + per - 1) / per, st);
   }
   if constexpr (kHas2) {
@@ -902,6 +906,7 @@ int ar2_dispatch(parseq_engine* e, pq::DecAr2Params& p, cudaStream_t st) {
     if (per > 32) per = 32;
     if (per < 17) per = 17;
     p.per = per;
+    e->ar_last_per = per; e->ar_last_ncl = (p.B + per - 1) / per;
     return ar2_launch<D, 2>(e, p, (p.B + per - 1) / per, st);
   }
   return PARSEQ_OK;
@@ -1541,6 +1546,18 @@ int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* ou
   return PARSEQ_OK;
 }
 
+int64_t parseq_debug_int(parseq_engine* e, const char* name) {
+  if (e == nullptr || name == nullptr) return -1;
+  const std::string n(name);
+  if (n == "ar2_clusters_mt1") return e->ar2_clusters[1];
+  if (n == "ar2_clusters_mt2") return e->ar2_clusters[2];
+  if (n == "ar2_occupancy_mt1") return e->ar2_occ[1];
+  if (n == "ar2_occupancy_mt2") return e->ar2_occ[2];
+  if (n == "ar_last_per") return e->ar_last_per;
+  if (n == "ar_last_clusters") return e->ar_last_ncl;
+  if (n == "sm_count") return e->lo.sm_count;
+  return -1;
+}
 int64_t parseq_kernel_launches(const parseq_engine* e) { return e ? e->launches : 0; }
 
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
