@@ -49,7 +49,6 @@ struct DecAr2Params {
 };
 
 constexpr int A2_THREADS = 256;
-constexpr int A2_CS = 8;            // CTAs per cluster
 constexpr int A2_SLOT = 16384;      // ring slot bytes
 constexpr int A2_SLOG_LD = 104;     // fp32 row pitch of the staged logits
 
@@ -86,13 +85,14 @@ __device__ __forceinline__ uint32_t box_off(int r, int c) {
   return static_cast<uint32_t>(r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1)));
 }
 
-template <int D, int MT>
+template <int D, int MT, int CS_>
 struct A2Cfg {
+  static constexpr int CS = CS_;                       // CTAs per cluster (8; 6 packs 23 instead of 15 clusters on a B200)
   static constexpr int ROWS = 16 * MT;                 // rows (images) per cluster, padded
-  static constexpr int OWN = ROWS / A2_CS;             // rows owned by one CTA for the attention phases
-  static constexpr int DS = D / A2_CS;                 // column slice of a D-wide projection
+  static constexpr int OWN = (ROWS + CS - 1) / CS;     // rows owned by one CTA for the attention phases
+  static constexpr int DS = D / CS;                    // column slice of a D-wide projection
   static constexpr int MD = 4 * D;                     // decoder MLP width (dec_mlp_ratio = 4)
-  static constexpr int MS = MD / A2_CS;                // hidden slice = D / 2
+  static constexpr int MS = MD / CS;                   // hidden slice
   static constexpr int KT = D / 64;                    // 64-wide k-blocks of a D-deep product
   static constexpr int KT2 = (MS + 63) / 64;           // k-blocks of the linear2 slice
   static constexpr int H = D / 32;                     // decoder heads (head_dim 32)
@@ -112,30 +112,31 @@ struct A2Cfg {
   static constexpr int Q_BYTES = OWN * D * 4;
   static constexpr int P_BYTES = 2 * MH * 16 * 256 * 2;   // P hi + lo, [16 MH, 256 keys] bf16
   static constexpr int CA_BYTES = D * 2;
-  static constexpr int ST_BYTES = A2_CS * ROWS * 8;
+  static constexpr int ST_BYTES = CS * ROWS * 8;
   static constexpr int RED_BYTES = 2 * 8 * MH * 16 * 4;
   static constexpr int IDS_BYTES = ROWS * 32 * 4;
   static constexpr int SLOG_BYTES = ROWS * A2_SLOG_LD * 4;
   static constexpr int MISC_BYTES = 1024;              // mbarriers, row statistics
+  static constexpr int QF_BYTES = KT * 16 * 16;        // bf16 hi / lo A-fragment words of one image's cross-attention query
   static constexpr int PL_BYTES = P_BYTES > SLOG_BYTES ? P_BYTES : SLOG_BYTES;   // P (cross-attention) and the staged logits (head) share
   static constexpr int FIXED = A_BYTES + R_BYTES + HD_BYTES + Y_BYTES + Q_BYTES + PL_BYTES + CA_BYTES + ST_BYTES + RED_BYTES +
-                               IDS_BYTES + MISC_BYTES + ROWS * 8;
+                               IDS_BYTES + MISC_BYTES + QF_BYTES + ROWS * 8;
   static constexpr int NSLOT_RAW = (232448 - 1024 - FIXED) / A2_SLOT;
   static constexpr int NSLOT = NSLOT_RAW > 8 ? 8 : NSLOT_RAW;
   static constexpr int SMEM = 1024 + NSLOT * A2_SLOT + FIXED;
   static_assert(NSLOT >= 3, "ring too shallow");
-  static_assert(DS % 8 == 0 && MS % 32 == 0, "slices");
+  static_assert(D % CS == 0 && DS % 8 == 0 && MS % 32 == 0, "slices");
   static_assert(DS * 128 <= A2_SLOT && NC1 * 128 <= A2_SLOT && NC2 * 128 <= A2_SLOT, "box fits a slot");
 };
 
-template <int D, int MT>
-constexpr size_t dec_ar2_smem_bytes() { return static_cast<size_t>(A2Cfg<D, MT>::SMEM); }
+template <int D, int MT, int CS>
+constexpr size_t dec_ar2_smem_bytes() { return static_cast<size_t>(A2Cfg<D, MT, CS>::SMEM); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // TMA ring: a static per-step program of slot fills; one thread issues, everybody consumes in program order.
-template <int D, int MT>
+template <int D, int MT, int CS>
 struct A2Ring {
-  using Cfg = A2Cfg<D, MT>;
+  using Cfg = A2Cfg<D, MT, CS>;
   uint8_t* slots;
   uint64_t* full;
   const DecAr2Maps* maps;
@@ -176,7 +177,7 @@ struct A2Ring {
       const int kb = j % Cfg::KT; j /= Cfg::KT;
       const int kv = j & 1;
       const int oi = j >> 1;
-      const int img = img0 + rank + A2_CS * oi;
+      const int img = img0 + rank + CS * oi;
       mbar_expect_tx(bar, static_cast<uint32_t>(tbox * 128));
       // column-blocked cache [2D/64][rows][64], row = image * T + key: one contiguous tbox x 128 B run (rows past the
       // image's T keys belong to the next image or are out of bounds: masked by the softmax)
@@ -210,9 +211,10 @@ struct A2Ring {
       if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
     }
   }
-  __device__ __forceinline__ const uint8_t* wait() {          // all threads
+  __device__ __forceinline__ const uint8_t* wait() {          // all threads; one lane per warp polls the barrier
     const int s = cons % Cfg::NSLOT;
-    mbar_wait(&full[s], static_cast<uint32_t>((cons / Cfg::NSLOT) & 1));
+    if ((threadIdx.x & 31) == 0) mbar_wait(&full[s], static_cast<uint32_t>((cons / Cfg::NSLOT) & 1));
+    __syncwarp();
     return slots + s * A2_SLOT;
   }
   __device__ __forceinline__ void release() {                  // all threads; the slot just consumed is refilled
@@ -262,10 +264,10 @@ __device__ __forceinline__ void mma_box(float (&acc)[NTW][4], const uint8_t* ati
   }
 }
 
-template <int D, int MT>
+template <int D, int MT, int CS>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
-  using Cfg = A2Cfg<D, MT>;
+  using Cfg = A2Cfg<D, MT, CS>;
   constexpr int ROWS = Cfg::ROWS, DS = Cfg::DS, KT = Cfg::KT, KT2 = Cfg::KT2, MS = Cfg::MS, MH = Cfg::MH, G = Cfg::G,
                 OWN = Cfg::OWN, H = Cfg::H;
   extern __shared__ uint8_t a2_smem_raw[];
@@ -285,15 +287,16 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   int* s_ids = reinterpret_cast<int*>(sm);                      sm += Cfg::IDS_BYTES;   // [ROWS][32]
   float* s_log = reinterpret_cast<float*>(s_p);
   float2* s_mr = reinterpret_cast<float2*>(sm);                 sm += ROWS * 8;         // per row (mean, rstd)
+  uint4* s_qf = reinterpret_cast<uint4*>(sm);                   sm += Cfg::QF_BYTES;    // [KT][4 k-steps][4 t]: hi01, hi89, lo01, lo89
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int rank = static_cast<int>(cluster_ctarank());
-  const int cl = blockIdx.x / A2_CS;
+  const int cl = blockIdx.x / CS;
   const int img0 = cl * p.per;
   const int nrows = (p.B - img0 < p.per) ? (p.B - img0) : p.per;    // images of this cluster (>= 1)
-  const int n_own = (nrows > rank) ? ((nrows - rank + A2_CS - 1) / A2_CS) : 0;
+  const int n_own = (nrows > rank) ? ((nrows - rank + CS - 1) / CS) : 0;
   const int mi = warp / G, ng = warp % G;                            // GEMM warp tiling: m16 tile, n group
 
   grid_dep_launch();
@@ -311,7 +314,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     const int r = i >> 5, c = i & 31;
     s_ids[i] = (r < nrows) ? p.ids[static_cast<long long>(img0 + r) * p.ids_ld + c] : 0;
   }
-  A2Ring<D, MT> ring;
+  A2Ring<D, MT, CS> ring;
   ring.init(s_ring, s_bar, &maps, rank, n_own, img0, p.tbox, p.tb, p.T, p.L);
   __syncthreads();
   ring.prologue();
@@ -322,7 +325,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   auto bcast16 = [&](uint8_t* buf, int r, int c, uint4 v) {
     const uint32_t off = smem_u32(buf) + a_off<ROWS>(r, c);
 #pragma unroll
-    for (int pe = 0; pe < A2_CS; ++pe) st_cluster_v4(mapa_cluster(off, static_cast<uint32_t>(pe)), v);
+    for (int pe = 0; pe < CS; ++pe) st_cluster_v4(mapa_cluster(off, static_cast<uint32_t>(pe)), v);
   };
   // per-row (mean, M2) of this CTA's y slice -> every CTA's s_st[rank]
   auto ln_stats = [&]() {
@@ -339,7 +342,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       for (int i = 0; i < DS / 8; ++i) { const float d = v[i] - mean; q += d * d; }
       q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
       // lane `sub` of the row group delivers to peer `sub`
-      st_cluster_v2f(mapa_cluster(smem_u32(&s_st[rank * ROWS + r]), static_cast<uint32_t>(sub)), mean, q);
+      if (sub < CS) st_cluster_v2f(mapa_cluster(smem_u32(&s_st[rank * ROWS + r]), static_cast<uint32_t>(sub)), mean, q);
     }
   };
   // merge the 8 slice statistics (fixed order: identical in every CTA), normalise this CTA's slice, all-gather bf16
@@ -347,7 +350,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     if (tid < ROWS) {
       float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < A2_CS; ++k) {
+      for (int k = 0; k < CS; ++k) {
         const float2 s = s_st[k * ROWS + tid];
         const float nb = static_cast<float>(DS), nn = n + nb;
         const float delta = s.x - mean;
@@ -384,6 +387,10 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     }
   };
 
+#define A2_PROF4(slot)                                                                                          \
+  do {                                                                                                          \
+    if (p.prof != nullptr && blockIdx.x == 0 && tid == 0 && step == 1) p.prof[26 * 16 + (slot)] = a2_timer_ns(); \
+  } while (0)
 #define A2_PROF(slot)                                                                                           \
   do {                                                                                                          \
     if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[step * 16 + (slot)] = a2_timer_ns();           \
@@ -401,7 +408,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
         const bool valid = it < items;
         const int itc = valid ? it : items - 1;
         const int oi = itc / (D / 8), ch = itc % (D / 8);
-        const int r = rank + A2_CS * oi;
+        const int r = rank + CS * oi;
         const int* idr = s_ids + r * 32;
         float q[8];
         {
@@ -494,9 +501,9 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           const int cg = rank * DS + nt * 8 + 2 * t;
           const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bq_c + cg));
           const int r0 = mi * 16 + g, r1 = r0 + 8;
-          st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r0 / A2_CS) * D + cg]), static_cast<uint32_t>(r0 % A2_CS)),
+          st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r0 / CS) * D + cg]), static_cast<uint32_t>(r0 % CS)),
                          (acc[j][0] + bb.x) * p.qscale, (acc[j][1] + bb.y) * p.qscale);
-          st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r1 / A2_CS) * D + cg]), static_cast<uint32_t>(r1 % A2_CS)),
+          st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r1 / CS) * D + cg]), static_cast<uint32_t>(r1 % CS)),
                          (acc[j][2] + bb.x) * p.qscale, (acc[j][3] + bb.y) * p.qscale);
         }
       }
@@ -508,9 +515,19 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     {
       const int ntk = p.tbox >> 6;                    // n8 tiles of keys per warp inside a key block (tbox / 8 warps / 8)
       const int kw = ntk * 8;                         // keys per warp per block
+      A2_PROF4(0);
       for (int oi = 0; oi < n_own; ++oi) {
-        const int r = rank + A2_CS * oi;
+        const int r = rank + CS * oi;
         const float* qrow = s_q + oi * D;
+        // the query's A-operand words, split into bf16 hi + lo (q = hi + lo to ~16 mantissa bits), once per image
+        for (int i = tid; i < KT * 16; i += A2_THREADS) {
+          const float* qd = qrow + (i >> 2) * 16 + 2 * (i & 3);        // (kb, ks) = i / 4, thread-in-quad t = i % 4
+          const float q0 = qd[0], q1 = qd[1], q8 = qd[8], q9 = qd[9];
+          const float h0 = __bfloat162float(__float2bfloat16_rn(q0)), h1 = __bfloat162float(__float2bfloat16_rn(q1));
+          const float h8 = __bfloat162float(__float2bfloat16_rn(q8)), h9 = __bfloat162float(__float2bfloat16_rn(q9));
+          s_qf[i] = make_uint4(pack_bf16(h0, h1), pack_bf16(h8, h9), pack_bf16(q0 - h0, q1 - h1), pack_bf16(q8 - h8, q9 - h9));
+        }
+        __syncthreads();
         float sacc[MH][2][2][4];                      // [m tile][key block][n8 tile][frag]; q_hi term
         float slo[MH][2][2][4];                       // q_lo term: its own dependency chain, added before the softmax
 #pragma unroll
@@ -533,14 +550,8 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const int hrow = (2 * kb + (ks >> 1)) & 15;           // row of this k-step's head inside its m tile
-                const float* qd = qrow + kb * 64 + ks * 16 + 2 * t;
-                const float q0 = qd[0], q1 = qd[1], q8 = qd[8], q9 = qd[9];
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(q0), h1 = __float2bfloat16_rn(q1), h8 = __float2bfloat16_rn(q8),
-                                    h9 = __float2bfloat16_rn(q9);
-                const uint32_t hi01 = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
-                const uint32_t hi89 = pack_bf16(__bfloat162float(h8), __bfloat162float(h9));
-                const uint32_t lo01 = pack_bf16(q0 - __bfloat162float(h0), q1 - __bfloat162float(h1));
-                const uint32_t lo89 = pack_bf16(q8 - __bfloat162float(h8), q9 - __bfloat162float(h9));
+                const uint4 qf = s_qf[(kb * 4 + ks) * 4 + t];
+                const uint32_t hi01 = qf.x, hi89 = qf.y, lo01 = qf.z, lo89 = qf.w;
                 const bool top = (g == hrow), bot = (g + 8 == hrow);
                 const uint32_t ah0 = top ? hi01 : 0u, ah1 = bot ? hi01 : 0u, ah2 = top ? hi89 : 0u, ah3 = bot ? hi89 : 0u;
                 const uint32_t al0 = top ? lo01 : 0u, al1 = bot ? lo01 : 0u, al2 = top ? lo89 : 0u, al3 = bot ? lo89 : 0u;
@@ -563,7 +574,8 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
             }
           }
         }
-        // ---- softmax over the keys (rows = heads): mask, cluster of 8 warps reduces through shared memory ----
+        if (oi < 4) A2_PROF4(1 + 3 * oi);
+        // ---- softmax over the keys (rows = heads): mask, the 8 warps reduce through shared memory ----
         float rmax[MH][2];
 #pragma unroll
         for (int a = 0; a < MH; ++a) {
@@ -639,6 +651,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           }
         }
         __syncthreads();
+        if (oi < 4) A2_PROF4(2 + 3 * oi);
         // ---- O = P V: V box kb holds dims [64 kb, +64); warp w -> dims 8 w .. 8 w + 7 of the box, head 2 kb + w / 4 ----
         for (int kb = 0; kb < KT; ++kb) {
           float oacc[4] = {0.f, 0.f, 0.f, 0.f}, oacc1[4] = {0.f, 0.f, 0.f, 0.f}, oacc2[4] = {0.f, 0.f, 0.f, 0.f},
@@ -689,6 +702,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
         }
         __syncthreads();
         for (int ch = tid; ch < D / 8; ch += A2_THREADS) bcast16(s_a2, r, ch * 8, *reinterpret_cast<const uint4*>(&s_ca[ch * 8]));
+        if (oi < 4) A2_PROF4(3 + 3 * oi);
       }
     }
     A2_PROF(7);
@@ -782,7 +796,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       const int c = i % DS;
       float s = s_recv[i];
 #pragma unroll
-      for (int k = 1; k < A2_CS; ++k) s += s_recv[k * ROWS * DS + i];
+      for (int k = 1; k < CS; ++k) s += s_recv[k * ROWS * DS + i];
       s_y[i] += s + __ldg(p.b2 + rank * DS + c);
     }
     __syncthreads();
@@ -821,7 +835,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       for (int r = warp; r < nrows; r += 8) {
         const long long b = img0 + r;
         float* lrow = p.logits + (b * p.L + step) * p.C;
-        const bool writer = (r % A2_CS) == rank;                        // one CTA stores the row
+        const bool writer = (r % CS) == rank;                        // one CTA stores the row
         float best = -INFINITY;
         int bi = 0x7fffffff;
         for (int j = lane; j < p.C; j += 32) {
@@ -847,6 +861,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     A2_PROF(15);
   }
 #undef A2_PROF
+#undef A2_PROF4
   cluster_sync_relacq();       // no CTA exits while a peer may still address its shared memory
 }
 

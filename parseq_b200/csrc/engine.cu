@@ -200,6 +200,20 @@ int ln_head_argmax_launch(const LaunchOpts& lo, const float* y, const float* g, 
   }
 }
 
+template <int D, int MT, int CS>
+int ar2_attr() {
+  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<D, MT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(pq::dec_ar2_smem_bytes<D, MT, CS>())));
+  return PARSEQ_OK;
+}
+int ar2_set_attributes() {
+  PQ_TRY((ar2_attr<192, 1, 8>())); PQ_TRY((ar2_attr<192, 2, 8>())); PQ_TRY((ar2_attr<384, 1, 8>())); PQ_TRY((ar2_attr<384, 2, 8>()));
+  PQ_TRY((ar2_attr<768, 1, 8>()));
+  PQ_TRY((ar2_attr<192, 1, 6>())); PQ_TRY((ar2_attr<192, 2, 6>())); PQ_TRY((ar2_attr<384, 1, 6>())); PQ_TRY((ar2_attr<384, 2, 6>()));
+  PQ_TRY((ar2_attr<768, 1, 6>()));
+  return PARSEQ_OK;
+}
+
 int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::ATC_SMEM_BYTES));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<192>())));
@@ -208,11 +222,7 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<384>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar_kernel<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar_smem_bytes<768>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<192, 1>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<192, 2>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<384, 1>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<384, 2>())));
-  PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pq::dec_ar2_smem_bytes<768, 1>())));
+  PQ_TRY(ar2_set_attributes());
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -398,11 +408,13 @@ struct parseq_engine {
   // persistent AR-loop kernel state (whole super-chunk)
   bool use_ar_kernel = true;
   int ar_impl = 2;                  // 2: cluster-owned kernel (dec_ar2.cuh), 1: grid-barrier kernel (dec_ar.cuh)
-  pq::DecAr2Maps ar2_maps;          // TMA descriptors of the decoder weights (built by parseq_finalize) and the K/V cache
+  pq::DecAr2Maps ar2_maps[2];       // TMA descriptors (decoder weights, K/V cache) for cluster size 8 [0] and 6 [1]
   bool ar2_maps_ok = false;
-  int ar2_clusters[3] = {0, 0, 0};  // max co-resident clusters of the MT = 1 / 2 instantiation (index = MT)
-  int ar2_occ[3] = {0, 0, 0};       // what cudaOccupancyMaxActiveClusters answered (debug)
+  int ar2_clusters[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // max co-resident clusters, index [MT][cluster size 6 ? 1 : 0]
+  int ar2_occ[3][2] = {{0, 0}, {0, 0}, {0, 0}};        // what cudaOccupancyMaxActiveClusters answered (debug)
+  int ar_last_cs = 0;
   int ar_last_per = 0, ar_last_ncl = 0;
+  int ar_cs = 0;                    // option "ar_cluster_size": 0 = auto, 6 / 8 = forced
   int ar_clusters_override = 0;     // option "ar_clusters": clusters the AR kernel spreads a batch over (0 = derived)
   int fuse_ln = 3;                  // bit 0: attn.proj, bit 1: mlp.fc2 also produce the LayerNorm that follows (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
@@ -827,89 +839,101 @@ bool ar2_supported(const parseq_engine* e) {
 int ar2_build_maps(parseq_engine* e) {
   const int D = e->D;
   const std::string Ly = "decoder.layers.0.";
-  const int DS = D / 8, MS = e->Md / 8;
-  const int NC1 = (MS % 128 == 0) ? 128 : 96, NC2 = (D % 128 == 0) ? 128 : 96;
-  PQ_TRY(make_tmap(&e->ar2_maps.wo_s, e->w(Ly + "self_attn.out_proj.weight"), 2, D, D, D, 64, DS));
-  PQ_TRY(make_tmap(&e->ar2_maps.wq_c, e->w(Ly + "cross_attn.in_proj_weight"), 2, D, D, D, 64, DS));
-  PQ_TRY(make_tmap(&e->ar2_maps.wo_c, e->w(Ly + "cross_attn.out_proj.weight"), 2, D, D, D, 64, DS));
-  PQ_TRY(make_tmap(&e->ar2_maps.w1, e->w(Ly + "linear1.weight"), 2, e->Md, D, D, 64, NC1));
-  PQ_TRY(make_tmap(&e->ar2_maps.w2, e->w(Ly + "linear2.weight"), 2, D, e->Md, e->Md, 64, NC2));
-  PQ_TRY(make_tmap(&e->ar2_maps.wh, e->w("head.weight"), 2, e->C, D, D, 64, 96));
-  const int tbox = e->T <= 64 ? 64 : 128;
-  const long long kv_rows = 1ll * e->max_batch * e->T;     // column-blocked cache [2D/64][kv_rows][64]
-  PQ_TRY(make_tmap3d(&e->ar2_maps.ckv, e->ckv, 64, kv_rows, 2 * D / 64, 64, 64 * kv_rows, 64, tbox));
+  for (int ci = 0; ci < 2; ++ci) {
+    const int cs = ci == 0 ? 8 : 6;
+    pq::DecAr2Maps& m = e->ar2_maps[ci];
+    const int DS = D / cs, MS = e->Md / cs;
+    const int NC1 = (MS % 128 == 0) ? 128 : 96, NC2 = (D % 128 == 0) ? 128 : 96;
+    PQ_TRY(make_tmap(&m.wo_s, e->w(Ly + "self_attn.out_proj.weight"), 2, D, D, D, 64, DS));
+    PQ_TRY(make_tmap(&m.wq_c, e->w(Ly + "cross_attn.in_proj_weight"), 2, D, D, D, 64, DS));
+    PQ_TRY(make_tmap(&m.wo_c, e->w(Ly + "cross_attn.out_proj.weight"), 2, D, D, D, 64, DS));
+    PQ_TRY(make_tmap(&m.w1, e->w(Ly + "linear1.weight"), 2, e->Md, D, D, 64, NC1));
+    PQ_TRY(make_tmap(&m.w2, e->w(Ly + "linear2.weight"), 2, D, e->Md, e->Md, 64, NC2));
+    PQ_TRY(make_tmap(&m.wh, e->w("head.weight"), 2, e->C, D, D, 64, 96));
+    const int tbox = e->T <= 64 ? 64 : 128;
+    const long long kv_rows = 1ll * e->max_batch * e->T;     // column-blocked cache [2D/64][kv_rows][64]
+    PQ_TRY(make_tmap3d(&m.ckv, e->ckv, 64, kv_rows, 2 * D / 64, 64, 64 * kv_rows, 64, tbox));
+  }
   e->ar2_maps_ok = true;
   return PARSEQ_OK;
 }
-template <int D, int MT>
-int ar2_launch(parseq_engine* e, const pq::DecAr2Params& p, int ncl, cudaStream_t st) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(ncl * pq::A2_CS));
+template <int D, int MT, int CS>
+void ar2_config(parseq_engine* e, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int ncl, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ncl * CS));
   cfg.blockDim = dim3(pq::A2_THREADS);
-  cfg.dynamicSmemBytes = pq::dec_ar2_smem_bytes<D, MT>();
+  cfg.dynamicSmemBytes = pq::dec_ar2_smem_bytes<D, MT, CS>();
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pq::A2_CS;
+  attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::dec_ar2_kernel<D, MT>, e->ar2_maps, p));
+}
+template <int D, int MT, int CS>
+int ar2_launch(parseq_engine* e, const pq::DecAr2Params& p, int ncl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  ar2_config<D, MT, CS>(e, cfg, attr, ncl, st);
+  e->ar_last_per = p.per; e->ar_last_ncl = ncl; e->ar_last_cs = CS;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::dec_ar2_kernel<D, MT, CS>, e->ar2_maps[CS == 6 ? 1 : 0], p));
   return PARSEQ_OK;
 }
-template <int D, int MT>
+// Clusters of this instantiation that can be co-resident.  A cluster lives inside one GPC; on the B200s of this pool the
+// occupancy query answers 15 for 8-CTA clusters (measured: 15 clusters run in 1.89 ms, 16 in 3.72 ms = two waves), so
+// 512 images do not fit one wave of 32-row clusters of 8; clusters of 6 pack more SMs (23 x 6 = 138).
+template <int D, int MT, int CS>
 int ar2_max_clusters(parseq_engine* e) {
-  if (e->ar2_clusters[MT] > 0) return e->ar2_clusters[MT];
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(e->lo.sm_count / pq::A2_CS * pq::A2_CS));
-  cfg.blockDim = dim3(pq::A2_THREADS);
-  cfg.dynamicSmemBytes = pq::dec_ar2_smem_bytes<D, MT>();
+  int& cache = e->ar2_clusters[MT][CS == 6 ? 1 : 0];
+  if (cache > 0) return cache;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pq::A2_CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  ar2_config<D, MT, CS>(e, cfg, attr, e->lo.sm_count / CS, nullptr);
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, pq::dec_ar2_kernel<D, MT>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, pq::dec_ar2_kernel<D, MT, CS>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
-    n = e->lo.sm_count / pq::A2_CS;
+    n = (CS == 8) ? (e->lo.sm_count / 10) : 1;   // unknown: a conservative guess for 8, "do not use" for 6
   }
-  e->ar2_occ[MT] = n;
-  // A cluster lives inside one GPC.  B200: 8 GPCs of 16 / 18 / 20 SMs -> two 8-CTA clusters each = 16 co-resident
-  // clusters, although the occupancy query answers floor(148 / 8) = 18: with 18 clusters launched the last two ran as a
-  // second wave and the kernel took twice as long (measured, bench r2d: 3.7 ms vs 1.9 ms).  Cap at 2 per GPC
-  // (GPC count estimated from the SM count; option "ar_clusters" overrides).
-  const int gpcs = (e->lo.sm_count + 9) / 18;
-  if (n > 2 * gpcs) n = 2 * gpcs;
+  e->ar2_occ[MT][CS == 6 ? 1 : 0] = n;
   if (e->ar_clusters_override > 0) n = e->ar_clusters_override;
-  e->ar2_clusters[MT] = n;
+  cache = n;
   return n;
 }
-// images per cluster: spread the batch over the clusters that can be co-resident (never more than 16 MT rows each)
+// Spread the batch over the co-resident clusters.  Candidates in order of per-step cost: clusters of 8 with one m16 row
+// tile, clusters of 8 with two, clusters of 6 (a third more weight bytes per CTA and step); the first that holds the
+// batch in ONE wave wins (the loop is latency-bound: a second wave doubles its time), else the fewest waves.
 template <int D>
 int ar2_dispatch(parseq_engine* e, pq::DecAr2Params& p, cudaStream_t st) {
   constexpr bool kHas2 = (D != 768);            // two m16 tiles of D = 768 rows do not fit shared memory
-  const int max1 = ar2_max_clusters<D, 1>(e);
-  int per = (p.B + max1 - 1) / max1;
-  if (per <= 16 || !kHas2) {
-    if (per > 16) per = 16;
-    p.per = per;
-    e->ar_last_per = per; e->ar_last_ncl = (p.B + per - 1) / per;
-    return ar2_launch<D, 1>(e, p, (p.B + per - 1) / per, st);
+  struct Cand { int mt, cs, maxc, rows; };
+  Cand c[4];
+  int nc = 0;
+  const bool allow6 = e->ar_cs != 8, allow8 = e->ar_cs != 6;
+  if (allow8) c[nc++] = Cand{1, 8, ar2_max_clusters<D, 1, 8>(e), 16};
+  if constexpr (kHas2) { if (allow8) c[nc++] = Cand{2, 8, ar2_max_clusters<D, 2, 8>(e), 32}; }
+  if (allow6) c[nc++] = Cand{1, 6, ar2_max_clusters<D, 1, 6>(e), 16};
+  if constexpr (kHas2) { if (allow6) c[nc++] = Cand{2, 6, ar2_max_clusters<D, 2, 6>(e), 32}; }
+  int best = -1, best_waves = 1 << 30;
+  for (int i = 0; i < nc; ++i) {
+    const int need = (p.B + c[i].rows - 1) / c[i].rows;             // clusters at full rows
+    const int waves = (need + c[i].maxc - 1) / c[i].maxc;
+    if (waves < best_waves) { best = i; best_waves = waves; }
   }
-  if constexpr (kHas2) {
-    const int max2 = ar2_max_clusters<D, 2>(e);
-    per = (p.B + max2 - 1) / max2;
-    if (per > 32) per = 32;
-    if (per < 17) per = 17;
-    p.per = per;
-    e->ar_last_per = per; e->ar_last_ncl = (p.B + per - 1) / per;
-    return ar2_launch<D, 2>(e, p, (p.B + per - 1) / per, st);
+  const Cand& k = c[best];
+  int per = (p.B + k.maxc * best_waves - 1) / (k.maxc * best_waves);   // even spread over the clusters of all waves
+  if (per > k.rows) per = k.rows;
+  if (per < 1) per = 1;
+  p.per = per;
+  const int ncl = (p.B + per - 1) / per;
+  if (k.cs == 8) {
+    if (k.mt == 1) return ar2_launch<D, 1, 8>(e, p, ncl, st);
+    if constexpr (kHas2) return ar2_launch<D, 2, 8>(e, p, ncl, st);
+  } else {
+    if (k.mt == 1) return ar2_launch<D, 1, 6>(e, p, ncl, st);
+    if constexpr (kHas2) return ar2_launch<D, 2, 6>(e, p, ncl, st);
   }
-  return PARSEQ_OK;
+  return fail(PARSEQ_ERR_STATE, "dec_ar2: no launch configuration");
 }
 
 // The whole AR loop (model.py:119-147) of B images in one persistent launch (csrc/dec_ar.cuh).
@@ -1549,10 +1573,11 @@ int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* ou
 int64_t parseq_debug_int(parseq_engine* e, const char* name) {
   if (e == nullptr || name == nullptr) return -1;
   const std::string n(name);
-  if (n == "ar2_clusters_mt1") return e->ar2_clusters[1];
-  if (n == "ar2_clusters_mt2") return e->ar2_clusters[2];
-  if (n == "ar2_occupancy_mt1") return e->ar2_occ[1];
-  if (n == "ar2_occupancy_mt2") return e->ar2_occ[2];
+  if (n == "ar2_occupancy_mt1_cs8") return e->ar2_occ[1][0];
+  if (n == "ar2_occupancy_mt2_cs8") return e->ar2_occ[2][0];
+  if (n == "ar2_occupancy_mt1_cs6") return e->ar2_occ[1][1];
+  if (n == "ar2_occupancy_mt2_cs6") return e->ar2_occ[2][1];
+  if (n == "ar_last_cluster_size") return e->ar_last_cs;
   if (n == "ar_last_per") return e->ar_last_per;
   if (n == "ar_last_clusters") return e->ar_last_ncl;
   if (n == "sm_count") return e->lo.sm_count;
@@ -1601,7 +1626,13 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (n == "ar_clusters") {
     if (value < 0 || value > 1024) return fail(PARSEQ_ERR_INVALID_ARG, "ar_clusters out of range");
     e->ar_clusters_override = static_cast<int>(value);
-    e->ar2_clusters[1] = e->ar2_clusters[2] = 0;
+    for (auto& r : e->ar2_clusters) r[0] = r[1] = 0;
+    drop_graphs(e);
+    return PARSEQ_OK;
+  }
+  if (n == "ar_cluster_size") {
+    if (value != 0 && value != 6 && value != 8) return fail(PARSEQ_ERR_INVALID_ARG, "ar_cluster_size: 0 (auto) / 6 / 8");
+    e->ar_cs = static_cast<int>(value);
     drop_graphs(e);
     return PARSEQ_OK;
   }

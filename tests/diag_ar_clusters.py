@@ -10,8 +10,9 @@ m = create_model("parseq", decode_ar=True, refine_iters=0); m.model.load_state_d
 m = m.eval().to("cuda")
 eng = m.model.engine()
 x = synth_images(cfg, 512, 1).cuda()
-def ar_ms(B, clusters):
+def ar_ms(B, clusters, cs=0):
     eng.set_option("ar_clusters", clusters)
+    eng.set_option("ar_cluster_size", cs)
     with torch.inference_mode():
         m(x[:B], 25); m(x[:B], 25)
         torch.cuda.synchronize()
@@ -22,6 +23,10 @@ def ar_ms(B, clusters):
         eng.set_option("timing", 0)
     return t, eng.debug_int("ar_last_per"), eng.debug_int("ar_last_clusters")
 print("sm_count", eng.debug_int("sm_count"))
-for B, c in [(32, 1), (64, 2), (128, 4), (256, 8), (288, 9), (320, 10), (384, 12), (448, 14), (480, 15), (512, 16), (512, 0), (256, 16), (128, 16), (512, 32)]:
-    t, per, ncl = ar_ms(B, c)
-    print(f"B={B:4d} ar_clusters={c:2d} -> per={per:2d} clusters={ncl:2d}  AR kernel {t:7.3f} ms   (occupancy query mt1/mt2: {eng.debug_int('ar2_occupancy_mt1')}/{eng.debug_int('ar2_occupancy_mt2')})")
+for B, c, cs in [(480, 0, 8), (512, 0, 8), (512, 0, 6), (512, 0, 0), (1, 0, 0), (16, 0, 0), (64, 0, 0), (240, 0, 0), (256, 0, 6), (736, 0, 6)]:
+    if B > 512:
+        continue
+    t, per, ncl = ar_ms(B, c, cs)
+    print(f"B={B:4d} forced cluster size {cs} -> cluster size {eng.debug_int('ar_last_cluster_size')} per={per:2d} clusters={ncl:2d}  AR kernel {t:7.3f} ms")
+print("occupancy query (clusters): cs8 mt1/mt2", eng.debug_int("ar2_occupancy_mt1_cs8"), eng.debug_int("ar2_occupancy_mt2_cs8"),
+      " cs6 mt1/mt2", eng.debug_int("ar2_occupancy_mt1_cs6"), eng.debug_int("ar2_occupancy_mt2_cs6"))

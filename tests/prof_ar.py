@@ -26,3 +26,10 @@ for step in (0, 1, 12, 13, 25):
     t = prof[step]
     print(f"step {step}: " + "  ".join(f"{names[k]}={(t[k+1]-t[k])/1000:.1f}" for k in range(15)), f" | total {(t[15]-t[0])/1000:.1f} us")
 print(f"whole loop: {(prof[25][15]-prof[0][0])/1000:.1f} us")
+if impl == 2:
+    t = prof[26]
+    if t[0]:
+        print("P4 detail (step 1, cluster 0 rank 0), us from P4 start; per owned image: K loop done, softmax done, V loop + broadcast done:")
+        print("  " + "  ".join(f"{(t[k]-t[0])/1000:.1f}" for k in range(1, 13) if t[k]))
+    print("cluster size", m.model.engine().debug_int("ar_last_cluster_size"), "rows/cluster", m.model.engine().debug_int("ar_last_per"),
+          "clusters", m.model.engine().debug_int("ar_last_clusters"))
