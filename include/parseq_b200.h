@@ -137,6 +137,10 @@ int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* ou
 
 /* Introspection used by bench.py / tests. */
 int64_t parseq_kernel_launches(const parseq_engine* e);      /* cumulative count of kernels launched */
+/* Microbenchmark of the AR kernel's TMA ring (tests/bench_tma_stream.py): `ctas` CTAs in clusters of `cluster` stream `nboxes`
+ * 16 KB boxes each from `buf` through `nslot` slots, no compute. */
+int parseq_bench_tma_stream(void* buf, int64_t bytes, int cluster, int ctas, int nboxes, int nslot, int mode, void* sink,
+                            parseq_stream_t stream);
 /* Debug counters by name ("ar2_occupancy_mt2", "ar2_clusters_mt2", "ar_last_per", "ar_last_clusters", "sm_count"); -1 if unknown. */
 int64_t parseq_debug_int(parseq_engine* e, const char* name);
 /* Options: "max_batch" (images per super-chunk = one CUDA graph), "chunk" (images per encoder pass inside a

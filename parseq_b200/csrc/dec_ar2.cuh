@@ -865,4 +865,43 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   cluster_sync_relacq();       // no CTA exits while a peer may still address its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Microbenchmark (tests/bench_tma_stream.py): the ring protocol of the AR kernel with no compute - every CTA streams
+// `nboxes` [128 x 64] bf16 boxes (16 KB) of a column-blocked buffer through `nslot` slots.  Launched with different
+// cluster sizes to measure what a CTA can ingest through TMA inside a cluster.
+__global__ void __launch_bounds__(A2_THREADS, 1)
+tma_stream_bench_kernel(const __grid_constant__ CUtensorMap map, int nboxes, int nslot, int row_boxes, int blocks, int mode,
+                        unsigned int* sink) {
+  extern __shared__ uint8_t bs_raw[];
+  const uint32_t raw = smem_u32(bs_raw);
+  uint8_t* sm = bs_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 12 * A2_SLOT);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < nslot; ++s) mbar_init(&bar[s], 1);
+    fence_mbar_init();
+    prefetch_tmap(&map);
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    const long long g = static_cast<long long>(blockIdx.x) * nboxes + i;
+    const int rb = static_cast<int>(g % row_boxes), blk = static_cast<int>((g / row_boxes) % blocks);
+    const int s = i % nslot;
+    mbar_expect_tx(&bar[s], A2_SLOT);
+    tma_load_3d(sm + s * A2_SLOT, &map, &bar[s], 0, rb * 128, blk);
+  };
+  if (tid == 0) for (int i = 0; i < nslot && i < nboxes; ++i) issue(i);
+  unsigned int acc = 0;
+  for (int i = 0; i < nboxes; ++i) {
+    const int s = i % nslot;
+    const uint32_t par = static_cast<uint32_t>((i / nslot) & 1);
+    if (mode & 1) { mbar_wait(&bar[s], par); }                  // every thread polls
+    else { if ((tid & 31) == 0) mbar_wait(&bar[s], par); __syncwarp(); }
+    acc += *reinterpret_cast<const unsigned int*>(sm + s * A2_SLOT + tid * 64);
+    __syncthreads();
+    if (i + nslot < nboxes && tid == (((i + nslot) & 7) << 5)) issue(i + nslot);
+  }
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
 }  // namespace pq

@@ -1570,6 +1570,34 @@ int parseq_text_embed(parseq_engine* e, int32_t n, const int32_t* ids, float* ou
   return PARSEQ_OK;
 }
 
+int parseq_bench_tma_stream(void* buf, int64_t bytes, int cluster, int ctas, int nboxes, int nslot, int mode, void* sink,
+                            parseq_stream_t stream) {
+  if (buf == nullptr || sink == nullptr || cluster < 1 || cluster > 8 || ctas % cluster != 0 || nslot < 1 || nslot > 12)
+    return fail(PARSEQ_ERR_INVALID_ARG, "bench_tma_stream: bad arguments");
+  const long long rows_total = 8192;                         // rows per 64-column block
+  const int blocks = static_cast<int>(bytes / (rows_total * 128));
+  if (blocks < 1) return fail(PARSEQ_ERR_INVALID_ARG, "bench_tma_stream: buffer too small");
+  CUtensorMap map;
+  PQ_TRY(make_tmap3d(&map, buf, 64, rows_total, blocks, 64, 64 * rows_total, 64, 128));
+  const int smem = 12 * pq::A2_SLOT + 1024 + 256;
+  PQ_CUDA(cudaFuncSetAttribute(pq::tma_stream_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(pq::A2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::tma_stream_bench_kernel, map, nboxes, nslot, static_cast<int>(rows_total / 128), blocks, mode,
+                             static_cast<unsigned int*>(sink)));
+  return PARSEQ_OK;
+}
+
 int64_t parseq_debug_int(parseq_engine* e, const char* name) {
   if (e == nullptr || name == nullptr) return -1;
   const std::string n(name);
