@@ -11,8 +11,7 @@
 //     cluster and step;
 //   * attention is split over images: CTA k owns rows k, k+8, ... ; cross-attention streams the image's K/V cache
 //     (T x 2D bf16) through the same ring and runs QK^T / PV as block-diagonal tensor-core products
-//     (rows = heads; q is split into bf16 hi + lo terms, i.e. ~16 mantissa bits; P is rounded to bf16 once, as in the
-//     encoder's attention);
+//     (rows = heads; q and P are split into bf16 hi + lo terms, i.e. ~16 mantissa bits);
 //   * the fp32 residual stream y lives column-sliced in the owning CTA; LayerNorm exchanges per-slice (mean, M2)
 //     through distributed shared memory (Chan merge in fixed order, identical in every CTA) and all-gathers the
 //     normalised bf16 rows, which are the A operand of the next projection;
@@ -111,7 +110,7 @@ struct A2Cfg {
   static constexpr int HD_BYTES = KT2 * ROWS * 128;
   static constexpr int Y_BYTES = ROWS * DS * 4;
   static constexpr int Q_BYTES = OWN * D * 4;
-  static constexpr int P_BYTES = MH * 16 * 256 * 2;       // P [16 MH, 256 keys] bf16 (un-normalised softmax numerators)
+  static constexpr int P_BYTES = 2 * MH * 16 * 256 * 2;   // P hi + lo, [16 MH, 256 keys] bf16
   static constexpr int CA_BYTES = D * 2;
   static constexpr int ST_BYTES = CS * ROWS * 8;
   static constexpr int RED_BYTES = 2 * 8 * MH * 16 * 4;
@@ -160,51 +159,47 @@ struct A2Ring {
     total = items_per_step * steps;
     cons = 0; prod = 0;
   }
-  // One ring item = up to 5 boxes of one tensor map landing back to back in a slot.
-  struct Desc {
-    const CUtensorMap* map;
-    uint8_t* dst;
-    uint64_t* bar;
-    int c0, c1, c2;          // coordinates of the first box (c2 < 0: 2D map)
-    int n, dc0, bytes;       // boxes, c0 step between boxes, bytes per box
-  };
-  __device__ Desc decode(int it, int s) const {
-    Desc d;
-    d.dst = slots + s * A2_SLOT; d.bar = &full[s]; d.c2 = -1; d.n = 1; d.dc0 = 64;
-    if (it < seg_c || (it >= seg_d && it < seg_e)) {        // D x D slices: k-blocks [j*GS, ...) of rows [rank*DS, +DS)
-      const int j = it < seg_b ? it : (it < seg_c ? it - seg_b : it - seg_d);
-      d.map = it < seg_b ? &maps->wo_s : (it < seg_c ? &maps->wq_c : &maps->wo_c);
-      const int k0 = j * Cfg::GS;
-      d.n = (Cfg::KT - k0 < Cfg::GS) ? (Cfg::KT - k0) : Cfg::GS;
-      d.c0 = k0 * 64; d.c1 = rank * Cfg::DS; d.bytes = Cfg::DS * 128;
-    } else if (it < seg_d) {                                 // K/V boxes: (own image, K|V, k-block, key block)
+  // D x D slice item j: k-blocks [j*GS, ...) of rows [rank*DS, +DS)
+  __device__ void issue_slice(const CUtensorMap* m, int j, uint8_t* dst, uint64_t* bar) {
+    const int k0 = j * Cfg::GS;
+    const int n = (Cfg::KT - k0 < Cfg::GS) ? (Cfg::KT - k0) : Cfg::GS;
+    mbar_expect_tx(bar, static_cast<uint32_t>(n * Cfg::DS * 128));
+    for (int i = 0; i < n; ++i) tma_load_2d(dst + i * Cfg::DS * 128, m, bar, (k0 + i) * 64, rank * Cfg::DS);
+  }
+  __device__ void issue(int it, int s) {       // one thread; it = item index inside the step, s = slot
+    uint8_t* dst = slots + s * A2_SLOT;
+    uint64_t* bar = &full[s];
+    if (it < seg_b) { issue_slice(&maps->wo_s, it, dst, bar); return; }
+    if (it < seg_c) { issue_slice(&maps->wq_c, it - seg_b, dst, bar); return; }
+    if (it < seg_d) {                    // K/V boxes: (own image, K|V, k-block, key block)
       int j = it - seg_c;
       const int t = j % tb; j /= tb;
       const int kb = j % Cfg::KT; j /= Cfg::KT;
-      const int kv = j & 1, oi = j >> 1;
+      const int kv = j & 1;
+      const int oi = j >> 1;
+      const int img = img0 + rank + CS * oi;
+      mbar_expect_tx(bar, static_cast<uint32_t>(tbox * 128));
       // column-blocked cache [2D/64][rows][64], row = image * T + key: one contiguous tbox x 128 B run (rows past the
       // image's T keys belong to the next image or are out of bounds: masked by the softmax)
-      d.map = &maps->ckv; d.c0 = 0; d.c1 = (img0 + rank + CS * oi) * T + t * 128; d.c2 = kv * Cfg::KT + kb; d.bytes = tbox * 128;
-    } else if (it < seg_f) {                                 // linear1: chunk c (NC1 rows of this CTA's hidden slice), k-block kb
+      tma_load_3d(dst, &maps->ckv, bar, 0, img * T + t * 128, kv * Cfg::KT + kb);
+      return;
+    }
+    if (it < seg_e) { issue_slice(&maps->wo_c, it - seg_d, dst, bar); return; }
+    if (it < seg_f) {                    // linear1: chunk c (NC1 rows of this CTA's hidden slice), k-block kb
       const int j = it - seg_e, c = j / Cfg::KT, kb = j % Cfg::KT;
-      d.map = &maps->w1; d.c0 = kb * 64; d.c1 = rank * Cfg::MS + c * Cfg::NC1; d.bytes = Cfg::NC1 * 128;
-    } else if (it < seg_g) {                                 // linear2: output chunk c (NC2 rows of W2), k-block kb of this CTA's K slice
+      mbar_expect_tx(bar, Cfg::NC1 * 128);
+      tma_load_2d(dst, &maps->w1, bar, kb * 64, rank * Cfg::MS + c * Cfg::NC1);
+      return;
+    }
+    if (it < seg_g) {                    // linear2: output chunk c (NC2 rows of W2), k-block kb of this CTA's K slice
       const int j = it - seg_f, c = j / Cfg::KT2, kb = j % Cfg::KT2;
-      d.map = &maps->w2; d.c0 = rank * Cfg::MS + kb * 64; d.c1 = c * Cfg::NC2; d.bytes = Cfg::NC2 * 128;
-    } else {                                                 // head: [96 x 64] (rows >= C zero-filled by the tensor map bounds)
-      d.map = &maps->wh; d.c0 = (it - seg_g) * 64; d.c1 = 0; d.bytes = 96 * 128;
+      mbar_expect_tx(bar, Cfg::NC2 * 128);
+      tma_load_2d(dst, &maps->w2, bar, rank * Cfg::MS + kb * 64, c * Cfg::NC2);
+      return;
     }
-    return d;
+    mbar_expect_tx(bar, 96 * 128);       // head: [96 x 64] (row 95.. zero-filled by the tensor map bounds)
+    tma_load_2d(dst, &maps->wh, bar, (it - seg_g) * 64, 0);
   }
-  __device__ __forceinline__ void fire(const Desc& d) const {       // one thread
-    mbar_expect_tx(d.bar, static_cast<uint32_t>(d.n * d.bytes));
-    if (d.c2 >= 0) {
-      tma_load_3d(d.dst, d.map, d.bar, d.c0, d.c1, d.c2);
-    } else {
-      for (int i = 0; i < d.n; ++i) tma_load_2d(d.dst + i * d.bytes, d.map, d.bar, d.c0 + i * d.dc0, d.c1);
-    }
-  }
-  __device__ void issue(int it, int s) const { fire(decode(it, s)); }
   // `prod` (items issued so far), its position inside the step and its slot advance identically in every thread; the
   // thread that issues rotates over the warps so that no warp carries the serial TMA-issue cost of every item
   int prod_it, prod_slot;
@@ -223,13 +218,9 @@ struct A2Ring {
     return slots + s * A2_SLOT;
   }
   __device__ __forceinline__ void release() {                  // all threads; the slot just consumed is refilled
-    // the thread whose turn it is decodes the next item while the other warps finish, fires right after the barrier
-    const bool mine = prod < total && threadIdx.x == ((prod & 7) << 5);
-    Desc d;
-    if (mine) d = decode(prod_it, prod_slot);
     __syncthreads();
     ++cons;
-    if (mine) fire(d);
+    if (prod < total && threadIdx.x == ((prod & 7) << 5)) issue(prod_it, prod_slot);
     ++prod;
     if (++prod_it == items_per_step) prod_it = 0;
     if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
@@ -636,13 +627,17 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
                 const float e2 = expf(sacc[a][tbi][c][2] - m1), e3 = expf(sacc[a][tbi][c][3] - m1);
                 rsum[a][0] += e0 + e1;
                 rsum[a][1] += e2 + e3;
-                // P -> A-operand tiles [16 MH rows][256 keys]: tile = key / 64
+                // P (hi, lo) -> A-operand tiles [16 MH rows][256 keys]: tile = key / 64
                 const int key = tbi * 128 + warp * kw + c * 8 + 2 * t;
                 const __nv_bfloat16 f0 = __float2bfloat16_rn(e0), f1 = __float2bfloat16_rn(e1), f2 = __float2bfloat16_rn(e2),
                                     f3 = __float2bfloat16_rn(e3);
                 const uint32_t off0 = a_off<MH * 16>(a * 16 + g, key), off1 = a_off<MH * 16>(a * 16 + g + 8, key);
                 *reinterpret_cast<uint32_t*>(s_p + off0) = pack_bf16(__bfloat162float(f0), __bfloat162float(f1));
                 *reinterpret_cast<uint32_t*>(s_p + off1) = pack_bf16(__bfloat162float(f2), __bfloat162float(f3));
+                *reinterpret_cast<uint32_t*>(s_p + Cfg::P_BYTES / 2 + off0) =
+                    pack_bf16(e0 - __bfloat162float(f0), e1 - __bfloat162float(f1));
+                *reinterpret_cast<uint32_t*>(s_p + Cfg::P_BYTES / 2 + off1) =
+                    pack_bf16(e2 - __bfloat162float(f2), e3 - __bfloat162float(f3));
               }
             }
 #pragma unroll
@@ -659,7 +654,8 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
         if (oi < 4) A2_PROF4(2 + 3 * oi);
         // ---- O = P V: V box kb holds dims [64 kb, +64); warp w -> dims 8 w .. 8 w + 7 of the box, head 2 kb + w / 4 ----
         for (int kb = 0; kb < KT; ++kb) {
-          float oacc[4] = {0.f, 0.f, 0.f, 0.f}, oacc1[4] = {0.f, 0.f, 0.f, 0.f};
+          float oacc[4] = {0.f, 0.f, 0.f, 0.f}, oacc1[4] = {0.f, 0.f, 0.f, 0.f}, oacc2[4] = {0.f, 0.f, 0.f, 0.f},
+                oacc3[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains: (P_hi, P_lo) x (even, odd k16 step)
           const int hh = 2 * kb + (warp >> 2);
           const int mh = hh >> 4, hrow = hh & 15;
 #pragma unroll
@@ -673,20 +669,27 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
                 uint32_t v0, v1, v2, v3;
                 ldmatrix_x4_trans(bbase + box_off(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4) * 16, warp * 8), v0, v1,
                                   v2, v3);
-                {
+#pragma unroll
+                for (int hl = 0; hl < 2; ++hl) {
                   uint32_t a0, a1, a2, a3, c0, c1, c2, c3;
-                  ldmatrix_x4(pbase + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + (lane >> 4) * 8), a0, a1, a2, a3);
-                  ldmatrix_x4(pbase + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + 16 + (lane >> 4) * 8), c0, c1, c2,
+                  const uint32_t po = pbase + hl * (Cfg::P_BYTES / 2);
+                  ldmatrix_x4(po + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                  ldmatrix_x4(po + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + 16 + (lane >> 4) * 8), c0, c1, c2,
                               c3);
-                  mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);          // two independent chains (even / odd k16 step)
-                  mma_bf16_16816(oacc1, c0, c1, c2, c3, v2, v3);
+                  if (hl == 0) {
+                    mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);
+                    mma_bf16_16816(oacc1, c0, c1, c2, c3, v2, v3);
+                  } else {
+                    mma_bf16_16816(oacc2, a0, a1, a2, a3, v0, v1);
+                    mma_bf16_16816(oacc3, c0, c1, c2, c3, v2, v3);
+                  }
                 }
               }
               ring.release();
             }
           }
 #pragma unroll
-          for (int f = 0; f < 4; ++f) oacc[f] += oacc1[f];
+          for (int f = 0; f < 4; ++f) oacc[f] = (oacc[f] + oacc1[f]) + (oacc2[f] + oacc3[f]);
           // the head's row of the 16 x 8 accumulator: (g == hrow) -> c0, c1; (g + 8 == hrow) -> c2, c3
           float tot = 0.f;
 #pragma unroll
@@ -866,37 +869,69 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
 // Microbenchmark (tests/bench_tma_stream.py): the ring protocol of the AR kernel with no compute - every CTA streams
 // `nboxes` [128 x 64] bf16 boxes (16 KB) of a column-blocked buffer through `nslot` slots.  Launched with different
 // cluster sizes to measure what a CTA can ingest through TMA inside a cluster.
-__global__ void __launch_bounds__(A2_THREADS, 1)
+__global__ void __launch_bounds__(A2_THREADS + 32, 1)
 tma_stream_bench_kernel(const __grid_constant__ CUtensorMap map, int nboxes, int nslot, int row_boxes, int blocks, int mode,
                         unsigned int* sink) {
+  // mode bit 0: every thread polls the full barrier (else one lane per warp); bit 1: a dedicated producer warp (warp 8)
+  // refills slots behind per-slot empty barriers, the 8 consumer warps never meet at a CTA barrier
   extern __shared__ uint8_t bs_raw[];
   const uint32_t raw = smem_u32(bs_raw);
   uint8_t* sm = bs_raw + (((raw + 1023u) & ~1023u) - raw);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 12 * A2_SLOT);
-  const int tid = threadIdx.x;
+  uint64_t* ebar = bar + 12;
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < nslot; ++s) mbar_init(&bar[s], 1);
+    for (int s = 0; s < nslot; ++s) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], 8); }
     fence_mbar_init();
     prefetch_tmap(&map);
   }
   __syncthreads();
-  auto issue = [&](int i) {
-    const long long g = static_cast<long long>(blockIdx.x) * nboxes + i;
-    const int rb = static_cast<int>(g % row_boxes), blk = static_cast<int>((g / row_boxes) % blocks);
-    const int s = i % nslot;
+  // box coordinates advance without divisions: (row box, block) of the i-th box of this CTA
+  int rb = static_cast<int>((static_cast<long long>(blockIdx.x) * nboxes) % row_boxes);
+  int blk = static_cast<int>(((static_cast<long long>(blockIdx.x) * nboxes) / row_boxes) % blocks);
+  auto issue = [&](int s) {
     mbar_expect_tx(&bar[s], A2_SLOT);
     tma_load_3d(sm + s * A2_SLOT, &map, &bar[s], 0, rb * 128, blk);
+    if (++rb == row_boxes) { rb = 0; if (++blk == blocks) blk = 0; }
   };
-  if (tid == 0) for (int i = 0; i < nslot && i < nboxes; ++i) issue(i);
   unsigned int acc = 0;
-  for (int i = 0; i < nboxes; ++i) {
-    const int s = i % nslot;
-    const uint32_t par = static_cast<uint32_t>((i / nslot) & 1);
-    if (mode & 1) { mbar_wait(&bar[s], par); }                  // every thread polls
-    else { if ((tid & 31) == 0) mbar_wait(&bar[s], par); __syncwarp(); }
-    acc += *reinterpret_cast<const unsigned int*>(sm + s * A2_SLOT + tid * 64);
-    __syncthreads();
-    if (i + nslot < nboxes && tid == (((i + nslot) & 7) << 5)) issue(i + nslot);
+  if (mode & 2) {
+    if (warp == 8) {
+      if ((tid & 31) == 0) {
+        for (int i = 0; i < nboxes; ++i) {
+          const int s = i % nslot;
+          if (i >= nslot) mbar_wait(&ebar[s], static_cast<uint32_t>(((i / nslot) - 1) & 1));
+          issue(s);
+        }
+      }
+    } else {
+      for (int i = 0; i < nboxes; ++i) {
+        const int s = i % nslot;
+        if ((tid & 31) == 0) mbar_wait(&bar[s], static_cast<uint32_t>((i / nslot) & 1));
+        __syncwarp();
+        acc += *reinterpret_cast<const unsigned int*>(sm + s * A2_SLOT + tid * 64);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&ebar[s]);
+      }
+    }
+  } else {
+    // every thread keeps the coordinate counters in step; thread 0 / the rotating thread issues
+    if (tid == 0) for (int i = 0; i < nslot && i < nboxes; ++i) issue(i);
+    else for (int i = 0; i < nslot && i < nboxes; ++i) { if (++rb == row_boxes) { rb = 0; if (++blk == blocks) blk = 0; } }
+    for (int i = 0; i < nboxes; ++i) {
+      const int s = i % nslot;
+      const uint32_t par = static_cast<uint32_t>((i / nslot) & 1);
+      if (warp < 8) {
+        if (mode & 1) { mbar_wait(&bar[s], par); }
+        else { if ((tid & 31) == 0) mbar_wait(&bar[s], par); __syncwarp(); }
+        acc += *reinterpret_cast<const unsigned int*>(sm + s * A2_SLOT + tid * 64);
+      }
+      __syncthreads();
+      if (i + nslot < nboxes) {
+        if (tid == (((i + nslot) & 7) << 5)) issue(s);
+        else if (++rb == row_boxes) { rb = 0; if (++blk == blocks) blk = 0; }
+      }
+    }
   }
   if (acc == 0x12345678u) sink[0] = acc;
 }

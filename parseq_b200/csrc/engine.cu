@@ -1583,7 +1583,7 @@ int parseq_bench_tma_stream(void* buf, int64_t bytes, int cluster, int ctas, int
   PQ_CUDA(cudaFuncSetAttribute(pq::tma_stream_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));
-  cfg.blockDim = dim3(pq::A2_THREADS);
+  cfg.blockDim = dim3(pq::A2_THREADS + 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];

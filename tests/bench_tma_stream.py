@@ -18,13 +18,11 @@ def run(mb, cluster, ctas, nboxes, nslot, mode=0):
     ms = a.elapsed_time(b) / 3
     per_sm = nboxes * 16384 / (ms * 1e-3) / 1e9
     return ms, per_sm, per_sm * ctas / 1e3
-print("working set  cluster ctas slots poll | ms/launch  GB/s per CTA  TB/s total   us per box")
+print("working set  cluster ctas slots mode            | ms/launch  GB/s per CTA  TB/s total   us per box")
+names = {0: "cta-barrier, lane poll", 1: "cta-barrier, all poll", 2: "producer warp"}
 for mb in (8, 1024):
-    for cluster, ctas in ((1, 120), (2, 120), (4, 120), (6, 120), (8, 120), (1, 8), (8, 8), (1, 1)):
+    for cluster, ctas in ((1, 120), (8, 120), (1, 1)):
         for nslot in (3, 6, 12):
-            ms, per, tot = run(mb, cluster, ctas, 2000, nslot)
-            print(f"{mb:6d} MB   {cluster:5d} {ctas:5d} {nslot:5d}  lane |  {ms:8.3f}   {per:9.1f}   {tot:8.2f}   {ms * 1000 / 2000:8.3f}")
-ms, per, tot = run(1024, 8, 120, 2000, 6, mode=1)
-print(f"  1024 MB       8   120     6  all  |  {ms:8.3f}   {per:9.1f}   {tot:8.2f}   {ms * 1000 / 2000:8.3f}")
-ms, per, tot = run(1024, 1, 120, 2000, 6, mode=1)
-print(f"  1024 MB       1   120     6  all  |  {ms:8.3f}   {per:9.1f}   {tot:8.2f}   {ms * 1000 / 2000:8.3f}")
+            for mode in (0, 2):
+                ms, per, tot = run(mb, cluster, ctas, 2000, nslot, mode)
+                print(f"{mb:6d} MB   {cluster:5d} {ctas:5d} {nslot:5d}  {names[mode]:22s} |  {ms:8.3f}   {per:9.1f}   {tot:8.2f}   {ms * 1000 / 2000:8.3f}")
