@@ -48,13 +48,20 @@ struct DecAr2Params {
   unsigned long long* prof;       // optional [L][16] globaltimer stamps of cluster 0 / rank 0, or nullptr
 };
 
-constexpr int A2_THREADS = 256;
+constexpr int A2_THREADS = 256;      // consumer threads (warps 0-7)
+constexpr int A2_LAUNCH_THREADS = 288;   // + warp 8: the TMA producer
 constexpr int A2_SLOT = 16384;      // ring slot bytes
 constexpr int A2_SLOG_LD = 104;     // fp32 row pitch of the staged logits
 
 __device__ __forceinline__ void cluster_sync_relacq() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// named barriers: 1 = the 8 consumer warps; 2 + s = "slot s is free" (consumers arrive, the producer warp waits)
+__device__ __forceinline__ void a2_csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void a2_slot_arrive(int s) { asm volatile("bar.arrive %0, 288;" ::"r"(2 + s) : "memory"); }
+__device__ __forceinline__ void a2_slot_wait(int s) { asm volatile("bar.sync %0, 288;" ::"r"(2 + s) : "memory"); }
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -200,30 +207,30 @@ struct A2Ring {
     mbar_expect_tx(bar, 96 * 128);       // head: [96 x 64] (row 95.. zero-filled by the tensor map bounds)
     tma_load_2d(dst, &maps->wh, bar, (it - seg_g) * 64, 0);
   }
-  // `prod` (items issued so far), its position inside the step and its slot advance identically in every thread; the
-  // thread that issues rotates over the warps so that no warp carries the serial TMA-issue cost of every item
+  // ---- producer warp (warp 8): issues every item in program order; item i >= NSLOT waits on the named barrier of its
+  //      slot until the 256 consumer threads have arrived there after item i - NSLOT
   int prod_it, prod_slot;
-  __device__ void prologue() {           // all threads (thread 0 issues)
-    prod_it = 0; prod_slot = 0;
-    for (; prod < Cfg::NSLOT && prod < total; ++prod) {
-      if (threadIdx.x == 0) issue(prod_it, prod_slot);
+  __device__ void producer_begin() { prod = 0; prod_it = 0; prod_slot = 0; }
+  __device__ __forceinline__ void produce(int n) {            // all 32 lanes of the producer warp
+    for (int k = 0; k < n; ++k) {
+      if (prod >= Cfg::NSLOT) a2_slot_wait(prod_slot);
+      if ((threadIdx.x & 31) == 0) issue(prod_it, prod_slot);
+      __syncwarp();
+      ++prod;
       if (++prod_it == items_per_step) prod_it = 0;
       if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
     }
   }
-  __device__ __forceinline__ const uint8_t* wait() {          // all threads; one lane per warp polls the barrier
+  // ---- consumer warps: no CTA-wide barrier per item
+  __device__ __forceinline__ const uint8_t* wait() {          // one lane per warp polls the barrier
     const int s = cons % Cfg::NSLOT;
     if ((threadIdx.x & 31) == 0) mbar_wait(&full[s], static_cast<uint32_t>((cons / Cfg::NSLOT) & 1));
     __syncwarp();
     return slots + s * A2_SLOT;
   }
-  __device__ __forceinline__ void release() {                  // all threads; the slot just consumed is refilled
-    __syncthreads();
+  __device__ __forceinline__ void release() {                  // this warp is done reading the slot
+    if (cons + Cfg::NSLOT < total) a2_slot_arrive(cons % Cfg::NSLOT);   // (the last NSLOT items are never refilled)
     ++cons;
-    if (prod < total && threadIdx.x == ((prod & 7) << 5)) issue(prod_it, prod_slot);
-    ++prod;
-    if (++prod_it == items_per_step) prod_it = 0;
-    if (++prod_slot == Cfg::NSLOT) prod_slot = 0;
   }
 };
 
@@ -265,7 +272,7 @@ __device__ __forceinline__ void mma_box(float (&acc)[NTW][4], const uint8_t* ati
 }
 
 template <int D, int MT, int CS>
-__global__ void __launch_bounds__(A2_THREADS, 1)
+__global__ void __launch_bounds__(A2_LAUNCH_THREADS, 1)
 dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   using Cfg = A2Cfg<D, MT, CS>;
   constexpr int ROWS = Cfg::ROWS, DS = Cfg::DS, KT = Cfg::KT, KT2 = Cfg::KT2, MS = Cfg::MS, MH = Cfg::MH, G = Cfg::G,
@@ -307,18 +314,51 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     prefetch_tmap(&maps.w2); prefetch_tmap(&maps.wh); prefetch_tmap(&maps.ckv);
   }
   // zero the A buffers once: padded rows (>= nrows) are multiplied but never stored; keep them finite
-  for (int i = tid; i < (Cfg::A_BYTES + Cfg::R_BYTES + Cfg::HD_BYTES) / 16; i += A2_THREADS)
+  for (int i = tid; i < (Cfg::A_BYTES + Cfg::R_BYTES + Cfg::HD_BYTES) / 16; i += A2_LAUNCH_THREADS)
     reinterpret_cast<uint4*>(s_a1)[i] = make_uint4(0u, 0u, 0u, 0u);
   grid_dep_wait();                    // weights / K/V cache / ids of the producing kernels are visible from here on
-  for (int i = tid; i < ROWS * 32; i += A2_THREADS) {
+  for (int i = tid; i < ROWS * 32; i += A2_LAUNCH_THREADS) {
     const int r = i >> 5, c = i & 31;
     s_ids[i] = (r < nrows) ? p.ids[static_cast<long long>(img0 + r) * p.ids_ld + c] : 0;
   }
   A2Ring<D, MT, CS> ring;
   ring.init(s_ring, s_bar, &maps, rank, n_own, img0, p.tbox, p.tb, p.T, p.L);
   __syncthreads();
-  ring.prologue();
   cluster_sync_relacq();              // every CTA of the cluster is running (remote stores are legal) and zero-filled
+
+  if (warp == 8) {
+    // ===================== TMA producer warp =====================
+    // Issues the step's items in program order, each as soon as its slot is free.  It joins every cluster barrier of
+    // the consumers, but arrives early and waits late (it touches no exchanged data), so that it runs up to one barrier
+    // interval ahead of them: the items of a phase are in flight while the consumers are still in the previous one.
+    ring.producer_begin();
+    bool pending = false;
+    auto csync_p = [&]() {
+      if (pending) cluster_wait_acquire();
+      cluster_arrive_release();
+      pending = true;
+    };
+    const int n_kv = ring.seg_d - ring.seg_c;
+    for (int step = 0; step < p.L; ++step) {
+      csync_p();                                                   // (1)
+      ring.produce(Cfg::NSL_S);                                    // P2: self-attention out-projection slice
+      csync_p();                                                   // (2)
+      csync_p();                                                   // (3)
+      ring.produce(Cfg::NSL_S);                                    // P3: cross-attention query-projection slice
+      csync_p();                                                   // (4)
+      ring.produce(n_kv);                                          // P4: K / V panels of the owned images
+      csync_p();                                                   // (5)
+      ring.produce(Cfg::NSL_S);                                    // P5: cross-attention out-projection slice
+      csync_p();                                                   // (6)
+      csync_p();                                                   // (7)
+      ring.produce(Cfg::NCH1 * KT + Cfg::NCH2 * KT2);              // P6 + P7: linear1 / linear2 slices
+      csync_p();                                                   // (8)
+      csync_p();                                                   // (9)
+      csync_p();                                                   // (10)
+      ring.produce(KT);                                            // P8: head
+    }
+    if (pending) cluster_wait_acquire();
+  } else {
 
   // ---- helpers -------------------------------------------------------------------------------------------------
   // all-gather 8 bf16 columns (16 B) of row r into `buf` of every CTA of the cluster
@@ -360,7 +400,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       }
       s_mr[tid] = make_float2(mean, 1.0f / sqrtf(m2 * (1.0f / D) + 1e-5f));
     }
-    __syncthreads();
+    a2_csync();
     for (int i = tid; i < ROWS * (DS / 8); i += A2_THREADS) {
       const int r = i / (DS / 8), ch = i % (DS / 8);
       const float2 mr = s_mr[r];
@@ -482,7 +522,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           *reinterpret_cast<float2*>(&s_y[(r0 + 8) * DS + c]) = make_float2(acc[j][2] + bb.x + pq2.x, acc[j][3] + bb.y + pq2.y);
         }
       }
-      __syncthreads();
+      a2_csync();
       ln_stats();
     }
     A2_PROF(3);
@@ -527,7 +567,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           const float h8 = __bfloat162float(__float2bfloat16_rn(q8)), h9 = __bfloat162float(__float2bfloat16_rn(q9));
           s_qf[i] = make_uint4(pack_bf16(h0, h1), pack_bf16(h8, h9), pack_bf16(q0 - h0, q1 - h1), pack_bf16(q8 - h8, q9 - h9));
         }
-        __syncthreads();
+        a2_csync();
         float sacc[MH][2][2][4];                      // [m tile][key block][n8 tile][frag]; q_hi term
         float slo[MH][2][2][4];                       // q_lo term: its own dependency chain, added before the softmax
 #pragma unroll
@@ -607,7 +647,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
             s_red[warp * (MH * 16) + a * 16 + g + 8] = rmax[a][1];
           }
         }
-        __syncthreads();
+        a2_csync();
         float rsum[MH][2];
 #pragma unroll
         for (int a = 0; a < MH; ++a) {
@@ -650,7 +690,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
             s_red[8 * MH * 16 + warp * (MH * 16) + a * 16 + g + 8] = rsum[a][1];
           }
         }
-        __syncthreads();
+        a2_csync();
         if (oi < 4) A2_PROF4(2 + 3 * oi);
         // ---- O = P V: V box kb holds dims [64 kb, +64); warp w -> dims 8 w .. 8 w + 7 of the box, head 2 kb + w / 4 ----
         for (int kb = 0; kb < KT; ++kb) {
@@ -700,7 +740,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           else if (g + 8 == hrow)
             *reinterpret_cast<uint32_t*>(&s_ca[kb * 64 + warp * 8 + 2 * t]) = pack_bf16(oacc[2] * inv, oacc[3] * inv);
         }
-        __syncthreads();
+        a2_csync();
         for (int ch = tid; ch < D / 8; ch += A2_THREADS) bcast16(s_a2, r, ch * 8, *reinterpret_cast<const uint4*>(&s_ca[ch * 8]));
         if (oi < 4) A2_PROF4(3 + 3 * oi);
       }
@@ -726,7 +766,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           *d1 = make_float2(o1.x + (acc[j][2] + bb.x), o1.y + (acc[j][3] + bb.y));
         }
       }
-      __syncthreads();
+      a2_csync();
       ln_stats();
     }
     A2_PROF(9);
@@ -759,7 +799,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           }
         }
       }
-      __syncthreads();
+      a2_csync();
     }
     A2_PROF(11);
     // ================= P7: partial linear2 over this CTA's K slice -> column owners =================
@@ -799,7 +839,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       for (int k = 1; k < CS; ++k) s += s_recv[k * ROWS * DS + i];
       s_y[i] += s + __ldg(p.b2 + rank * DS + c);
     }
-    __syncthreads();
+    a2_csync();
     ln_stats();
     A2_PROF(13);
     cluster_sync_relacq();                                                                            // (9) LN3 statistics
@@ -831,7 +871,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           s_log[(r0 + 8) * A2_SLOG_LD + c + 1] = acc[j][3] + b1;
         }
       }
-      __syncthreads();
+      a2_csync();
       for (int r = warp; r < nrows; r += 8) {
         const long long b = img0 + r;
         float* lrow = p.logits + (b * p.L + step) * p.C;
@@ -856,12 +896,13 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           if (writer) p.ids[b * p.ids_ld + step + 1] = v;
         }
       }
-      __syncthreads();
+      a2_csync();
     }
     A2_PROF(15);
   }
 #undef A2_PROF
 #undef A2_PROF4
+  }
   cluster_sync_relacq();       // no CTA exits while a peer may still address its shared memory
 }
 

@@ -861,7 +861,7 @@ template <int D, int MT, int CS>
 void ar2_config(parseq_engine* e, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int ncl, cudaStream_t st) {
   cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3(static_cast<unsigned>(ncl * CS));
-  cfg.blockDim = dim3(pq::A2_THREADS);
+  cfg.blockDim = dim3(pq::A2_LAUNCH_THREADS);
   cfg.dynamicSmemBytes = pq::dec_ar2_smem_bytes<D, MT, CS>();
   cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
