@@ -698,31 +698,37 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
                 oacc3[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains: (P_hi, P_lo) x (even, odd k16 step)
           const int hh = 2 * kb + (warp >> 2);
           const int mh = hh >> 4, hrow = hh & 15;
+          // lane constants of the operand addresses (both layouts are 128B-swizzled rows of 128 B):
+          //   V box rows = keys: row kk*16 + vrow, 16-byte chunk `warp` (dims 8 warp ..) -> ((warp ^ (vrow & 7)) << 4)
+          //   P tiles [16 MH rows][64 keys]: row mh*16 + prow, chunk (key/8 + lane>>4) -> ((c ^ (lane>>4) ^ (prow & 7)) << 4), c even
+          const int vrow = (lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4) * 16;
+          const uint32_t voff = static_cast<uint32_t>(vrow * 128 + ((warp ^ (vrow & 7)) << 4));
+          const int prow = (lane & 7) + ((lane >> 3) & 1) * 8;
+          const uint32_t poff = smem_u32(s_p) + static_cast<uint32_t>((mh * 16 + prow) * 128);
+          const uint32_t pxor = static_cast<uint32_t>(((lane >> 4) ^ (prow & 7)) << 4);
 #pragma unroll
           for (int tbi = 0; tbi < 2; ++tbi) {
             if (tbi < p.tb) {
               const uint8_t* box = ring.wait();
-              const uint32_t bbase = smem_u32(box);
-              const uint32_t pbase = smem_u32(s_p);
-              for (int kk = 0; kk < p.tbox / 16; kk += 2) {           // two k16 steps per ldmatrix.x4.trans of V
-                const int key0 = tbi * 128 + kk * 16;
-                uint32_t v0, v1, v2, v3;
-                ldmatrix_x4_trans(bbase + box_off(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4) * 16, warp * 8), v0, v1,
-                                  v2, v3);
+              const uint32_t bbase = smem_u32(box) + voff;
 #pragma unroll
-                for (int hl = 0; hl < 2; ++hl) {
+              for (int kk = 0; kk < 8; kk += 2) {                     // two k16 steps per ldmatrix.x4.trans of V
+                if (kk * 16 < p.tbox) {                               // uniform (tbox = 64 or 128)
+                  uint32_t v0, v1, v2, v3;
+                  ldmatrix_x4_trans(bbase + kk * 16 * 128, v0, v1, v2, v3);
+                  // keys tbi*128 + kk*16 .. +31: P tile (tbi*2 + kk/4), chunks (kk & 3) * 2 and + 2
+                  const uint32_t pt = poff + static_cast<uint32_t>((tbi * 2 + (kk >> 2)) * (MH * 16 * 128));
+                  const uint32_t pa = pt + ((static_cast<uint32_t>(((kk & 3) * 2) << 4)) ^ pxor);
+                  const uint32_t pc = pt + ((static_cast<uint32_t>(((kk & 3) * 2 + 2) << 4)) ^ pxor);
                   uint32_t a0, a1, a2, a3, c0, c1, c2, c3;
-                  const uint32_t po = pbase + hl * (Cfg::P_BYTES / 2);
-                  ldmatrix_x4(po + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + (lane >> 4) * 8), a0, a1, a2, a3);
-                  ldmatrix_x4(po + a_off<MH * 16>(mh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, key0 + 16 + (lane >> 4) * 8), c0, c1, c2,
-                              c3);
-                  if (hl == 0) {
-                    mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);
-                    mma_bf16_16816(oacc1, c0, c1, c2, c3, v2, v3);
-                  } else {
-                    mma_bf16_16816(oacc2, a0, a1, a2, a3, v0, v1);
-                    mma_bf16_16816(oacc3, c0, c1, c2, c3, v2, v3);
-                  }
+                  ldmatrix_x4(pa, a0, a1, a2, a3);
+                  ldmatrix_x4(pc, c0, c1, c2, c3);
+                  mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);
+                  mma_bf16_16816(oacc1, c0, c1, c2, c3, v2, v3);
+                  ldmatrix_x4(pa + Cfg::P_BYTES / 2, a0, a1, a2, a3);   // lo terms of P
+                  ldmatrix_x4(pc + Cfg::P_BYTES / 2, c0, c1, c2, c3);
+                  mma_bf16_16816(oacc2, a0, a1, a2, a3, v0, v1);
+                  mma_bf16_16816(oacc3, c0, c1, c2, c3, v2, v3);
                 }
               }
               ring.release();
