@@ -124,10 +124,11 @@ struct A2Cfg {
   static constexpr int IDS_BYTES = ROWS * 32 * 4;
   static constexpr int SLOG_BYTES = ROWS * A2_SLOG_LD * 4;
   static constexpr int MISC_BYTES = 1024;              // mbarriers, row statistics
+  static constexpr int PART_BYTES = 8 * D * 4;         // cross-attention partial outputs of the 8 key slices (one image)
   static constexpr int QF_BYTES = KT * 16 * 16;        // bf16 hi / lo A-fragment words of one image's cross-attention query
   static constexpr int PL_BYTES = P_BYTES > SLOG_BYTES ? P_BYTES : SLOG_BYTES;   // P (cross-attention) and the staged logits (head) share
   static constexpr int FIXED = A_BYTES + R_BYTES + HD_BYTES + Y_BYTES + Q_BYTES + PL_BYTES + CA_BYTES + ST_BYTES + RED_BYTES +
-                               IDS_BYTES + MISC_BYTES + QF_BYTES + ROWS * 8;
+                               IDS_BYTES + MISC_BYTES + QF_BYTES + PART_BYTES + ROWS * 8;
   static constexpr int NSLOT_RAW = (232448 - 1024 - FIXED) / A2_SLOT;
   static constexpr int NSLOT = NSLOT_RAW > 8 ? 8 : NSLOT_RAW;
   static constexpr int SMEM = 1024 + NSLOT * A2_SLOT + FIXED;
@@ -295,6 +296,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   float* s_log = reinterpret_cast<float*>(s_p);
   float2* s_mr = reinterpret_cast<float2*>(sm);                 sm += ROWS * 8;         // per row (mean, rstd)
   uint4* s_qf = reinterpret_cast<uint4*>(sm);                   sm += Cfg::QF_BYTES;    // [KT][4 k-steps][4 t]: hi01, hi89, lo01, lo89
+  float* s_part = reinterpret_cast<float*>(sm);                 sm += Cfg::PART_BYTES;  // [8 warps][D]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -692,59 +694,79 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
         }
         a2_csync();
         if (oi < 4) A2_PROF4(2 + 3 * oi);
-        // ---- O = P V: V box kb holds dims [64 kb, +64); warp w -> dims 8 w .. 8 w + 7 of the box, head 2 kb + w / 4 ----
-        for (int kb = 0; kb < KT; ++kb) {
-          float oacc[4] = {0.f, 0.f, 0.f, 0.f}, oacc1[4] = {0.f, 0.f, 0.f, 0.f}, oacc2[4] = {0.f, 0.f, 0.f, 0.f},
-                oacc3[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains: (P_hi, P_lo) x (even, odd k16 step)
-          const int hh = 2 * kb + (warp >> 2);
-          const int mh = hh >> 4, hrow = hh & 15;
-          // lane constants of the operand addresses (both layouts are 128B-swizzled rows of 128 B):
-          //   V box rows = keys: row kk*16 + vrow, 16-byte chunk `warp` (dims 8 warp ..) -> ((warp ^ (vrow & 7)) << 4)
-          //   P tiles [16 MH rows][64 keys]: row mh*16 + prow, chunk (key/8 + lane>>4) -> ((c ^ (lane>>4) ^ (prow & 7)) << 4), c even
-          const int vrow = (lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4) * 16;
-          const uint32_t voff = static_cast<uint32_t>(vrow * 128 + ((warp ^ (vrow & 7)) << 4));
+        // ---- O = P V, split over the KEYS: warp w owns the k16 step w of every key block, so its P fragments (hi + lo)
+        // are loaded once per image and every V box is read from shared memory exactly once (a split over the dims re-read
+        // the whole P tile in every warp for every box: 4x the box's own bytes).  Per box: 64 dims = 8 n8 tiles; the two
+        // heads' rows of the 16 x 64 partial product go to s_part[warp], summed over the warps after the last box.
+        {
+          const int nsteps = p.tbox >> 4;                      // k16 steps per key block (4 or 8)
+          const bool has_step = warp < nsteps;
           const int prow = (lane & 7) + ((lane >> 3) & 1) * 8;
-          const uint32_t poff = smem_u32(s_p) + static_cast<uint32_t>((mh * 16 + prow) * 128);
-          const uint32_t pxor = static_cast<uint32_t>(((lane >> 4) ^ (prow & 7)) << 4);
+          uint32_t ph[2][4], pl[2][4];                         // [key block][frag]
+          int cur_mh = -1;
+          for (int kb = 0; kb < KT; ++kb) {
+            const int mh = (2 * kb) >> 4;
+            if (mh != cur_mh) {                                // (re)load this warp's P fragments for the m16 tile of heads
+              cur_mh = mh;
 #pragma unroll
-          for (int tbi = 0; tbi < 2; ++tbi) {
-            if (tbi < p.tb) {
-              const uint8_t* box = ring.wait();
-              const uint32_t bbase = smem_u32(box) + voff;
-#pragma unroll
-              for (int kk = 0; kk < 8; kk += 2) {                     // two k16 steps per ldmatrix.x4.trans of V
-                if (kk * 16 < p.tbox) {                               // uniform (tbox = 64 or 128)
-                  uint32_t v0, v1, v2, v3;
-                  ldmatrix_x4_trans(bbase + kk * 16 * 128, v0, v1, v2, v3);
-                  // keys tbi*128 + kk*16 .. +31: P tile (tbi*2 + kk/4), chunks (kk & 3) * 2 and + 2
-                  const uint32_t pt = poff + static_cast<uint32_t>((tbi * 2 + (kk >> 2)) * (MH * 16 * 128));
-                  const uint32_t pa = pt + ((static_cast<uint32_t>(((kk & 3) * 2) << 4)) ^ pxor);
-                  const uint32_t pc = pt + ((static_cast<uint32_t>(((kk & 3) * 2 + 2) << 4)) ^ pxor);
-                  uint32_t a0, a1, a2, a3, c0, c1, c2, c3;
-                  ldmatrix_x4(pa, a0, a1, a2, a3);
-                  ldmatrix_x4(pc, c0, c1, c2, c3);
-                  mma_bf16_16816(oacc, a0, a1, a2, a3, v0, v1);
-                  mma_bf16_16816(oacc1, c0, c1, c2, c3, v2, v3);
-                  ldmatrix_x4(pa + Cfg::P_BYTES / 2, a0, a1, a2, a3);   // lo terms of P
-                  ldmatrix_x4(pc + Cfg::P_BYTES / 2, c0, c1, c2, c3);
-                  mma_bf16_16816(oacc2, a0, a1, a2, a3, v0, v1);
-                  mma_bf16_16816(oacc3, c0, c1, c2, c3, v2, v3);
+              for (int tbi = 0; tbi < 2; ++tbi) {
+                if (tbi < p.tb && has_step) {
+                  const uint32_t pa = smem_u32(s_p) + a_off<MH * 16>(mh * 16 + prow, tbi * 128 + warp * 16 + (lane >> 4) * 8);
+                  ldmatrix_x4(pa, ph[tbi][0], ph[tbi][1], ph[tbi][2], ph[tbi][3]);
+                  ldmatrix_x4(pa + Cfg::P_BYTES / 2, pl[tbi][0], pl[tbi][1], pl[tbi][2], pl[tbi][3]);
                 }
               }
-              ring.release();
+            }
+            float oacc[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+#pragma unroll
+            for (int tbi = 0; tbi < 2; ++tbi) {
+              if (tbi < p.tb) {
+                const uint8_t* box = ring.wait();
+                if (has_step) {
+                  const int vr = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;      // key row of this lane's 8x8 matrix
+                  const uint32_t vb = smem_u32(box) + static_cast<uint32_t>(vr * 128);
+                  const uint32_t vx = static_cast<uint32_t>(vr & 7);
+#pragma unroll
+                  for (int np = 0; np < 4; ++np) {                                     // dims 16 np .. 16 np + 15 of the box
+                    uint32_t v0, v1, v2, v3;
+                    ldmatrix_x4_trans(vb + (((static_cast<uint32_t>(np * 2) + (lane >> 4)) ^ vx) << 4), v0, v1, v2, v3);
+                    mma_bf16_16816(oacc[2 * np], ph[tbi][0], ph[tbi][1], ph[tbi][2], ph[tbi][3], v0, v1);
+                    mma_bf16_16816(oacc[2 * np + 1], ph[tbi][0], ph[tbi][1], ph[tbi][2], ph[tbi][3], v2, v3);
+                    mma_bf16_16816(oacc[2 * np], pl[tbi][0], pl[tbi][1], pl[tbi][2], pl[tbi][3], v0, v1);
+                    mma_bf16_16816(oacc[2 * np + 1], pl[tbi][0], pl[tbi][1], pl[tbi][2], pl[tbi][3], v2, v3);
+                  }
+                }
+                ring.release();
+              }
+            }
+            // rows of the two heads of this box: n8 tiles 0..3 -> head 2 kb, tiles 4..7 -> head 2 kb + 1
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int hr = (2 * kb + (j >> 2)) & 15;
+              if ((hr & 7) == g) {
+                const float2 v = (hr < 8) ? make_float2(oacc[j][0], oacc[j][1]) : make_float2(oacc[j][2], oacc[j][3]);
+                *reinterpret_cast<float2*>(&s_part[warp * D + kb * 64 + j * 8 + 2 * t]) = has_step ? v : make_float2(0.f, 0.f);
+              }
             }
           }
+          a2_csync();
+          // sum the 8 key slices (fixed order), normalise by the row sum of the head, round to bf16
+          for (int i = tid; i < D / 2; i += A2_THREADS) {
+            const int d0 = 2 * i, hh = d0 >> 5;
+            float tot = 0.f;
 #pragma unroll
-          for (int f = 0; f < 4; ++f) oacc[f] = (oacc[f] + oacc1[f]) + (oacc2[f] + oacc3[f]);
-          // the head's row of the 16 x 8 accumulator: (g == hrow) -> c0, c1; (g + 8 == hrow) -> c2, c3
-          float tot = 0.f;
+            for (int w = 0; w < 8; ++w) tot += s_red[8 * MH * 16 + w * (MH * 16) + hh];
+            float2 o = *reinterpret_cast<const float2*>(&s_part[d0]);
 #pragma unroll
-          for (int w = 0; w < 8; ++w) tot += s_red[8 * MH * 16 + w * (MH * 16) + mh * 16 + hrow];
-          const float inv = 1.0f / tot;
-          if (g == hrow)
-            *reinterpret_cast<uint32_t*>(&s_ca[kb * 64 + warp * 8 + 2 * t]) = pack_bf16(oacc[0] * inv, oacc[1] * inv);
-          else if (g + 8 == hrow)
-            *reinterpret_cast<uint32_t*>(&s_ca[kb * 64 + warp * 8 + 2 * t]) = pack_bf16(oacc[2] * inv, oacc[3] * inv);
+            for (int w = 1; w < 8; ++w) {
+              const float2 q2 = *reinterpret_cast<const float2*>(&s_part[w * D + d0]);
+              o.x += q2.x; o.y += q2.y;
+            }
+            const float inv = 1.0f / tot;
+            *reinterpret_cast<uint32_t*>(&s_ca[d0]) = pack_bf16(o.x * inv, o.y * inv);
+          }
         }
         a2_csync();
         for (int ch = tid; ch < D / 8; ch += A2_THREADS) bcast16(s_a2, r, ch * 8, *reinterpret_cast<const uint4*>(&s_ca[ch * 8]));
