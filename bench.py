@@ -545,10 +545,11 @@ def main():
               "avg_dram_bytes_per_launch"),
         entry("enc_gemm_ln", "hbm", "gemm_ln_fused_kernel (attn.proj / mlp.fc2 + residual + following LayerNorm)",
               (fused_bytes(D_) + fused_bytes(D_ * cfg.enc_mlp_ratio)) * (n_fused / 2.0), "GB/s", "fused_avg_dram_bytes_per_launch"),
-        entry("dec_ar", "hbm", "dec_ar2_kernel (whole AR loop: 26 steps, cluster-owned)" if args.ar_kernel in (-1, 2)
-              else "dec_ar_kernel (whole AR loop, grid barriers)", ar_bytes * tim.get("dec_ar", {}).get("launches", 0), "GB/s",
-              "dec_ar_dram_bytes_per_launch",
-              note="bytes = 26 x (cross K/V cache of the batch + context K/V rows + decoder weights + logits row); "
+        entry("dec_ar", "hbm", "dec_ar2_kernel (whole AR loop: 26 steps; independent clusters of 6 / 8 CTAs, TMA producer warp)"
+              if args.ar_kernel in (-1, 2) else "dec_ar_kernel (whole AR loop, grid barriers)",
+              ar_bytes * tim.get("dec_ar", {}).get("launches", 0), "GB/s", "dec_ar_dram_bytes_per_launch",
+              note="bytes = 26 x (cross K/V cache of the batch + context K/V rows + decoder weights + logits row); the loop is "
+                   "a chain of 26 x 11 dependent phases per cluster (latency-bound: profiles/r2_ar_phase_stamps_bs512.txt), "
                    "tensor view: see tflops"),
         entry("enc_attn", "hbm", "enc_attention_tc_kernel (QK^T, softmax, PV per (image, head))",
               (Mrows * 3 * D_ * 2 + Mrows * D_ * 2) * tim["enc_attn"]["launches"], "GB/s", "attn_dram_bytes_per_launch"),

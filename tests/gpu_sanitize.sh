@@ -1,7 +1,8 @@
 #!/bin/bash
+# compute-sanitizer over the final build: all decode modes at B=3 (fused residual-GEMM + LayerNorm forced, tcgen05 attention,
+# cluster AR kernel incl. the producer warp / DSMEM exchanges), the grid-barrier AR kernel, the decode API.
 mkdir -p gpurun_out
 for tool in memcheck synccheck racecheck; do
-  echo "== compute-sanitizer --tool $tool"
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tests/sanitize_small.py > gpurun_out/sanitize_$tool.log 2>&1
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_small done|Error|error" gpurun_out/sanitize_$tool.log | head -8
+  echo "== compute-sanitizer --tool $tool" | tee -a gpurun_out/r2_compute_sanitizer.txt
+  timeout 900 compute-sanitizer --tool $tool python tests/sanitize_small.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|error|hazard|ok:|Traceback" | head -20 | tee -a gpurun_out/r2_compute_sanitizer.txt
 done
