@@ -434,6 +434,8 @@ struct parseq_engine {
   std::vector<Stage> stages;
   int max_batch = 512;              // images per graph / super-chunk = stages.size() * chunk
   cudaStream_t main = nullptr;      // engine-owned: user stream -> (event) -> main -> (event) -> user stream
+  cudaStream_t copy = nullptr;      // host entry points: input upload in two halves, overlapped with the first half's encoder
+  cudaEvent_t ev_c[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // static I/O buffers the CUDA graphs are captured on
   float* in_images = nullptr; float* out_logits = nullptr; int* out_ids = nullptr; int* out_steps = nullptr;
@@ -583,7 +585,9 @@ int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float
 
 // ---------------------------------------------------------------- encoder (model.py:83-84 -> timm forward_features)
 int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_bfloat16* mem_out, float* memory32,
-                 cudaStream_t st, bool final_norm = true) {
+                 cudaStream_t st, bool final_norm = true, int regime_batch = 0) {
+  // regime_batch: the batch whose size selects the kernel variants (a half batch encoded on its own, under the upload of
+  // the other half, must run the kernels the whole batch would: rows stay bit-identical to the unsplit call)
   const int D = e->D, T = e->T, M = B * T;
   e->cur_cat = CAT_ENC_GEMM;
   {
@@ -625,7 +629,8 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
   // The fused kernel owns whole 128-row tiles (one CTA per tile, both column halves in sequence): it pays off once
   // the tiles fill the machine about twice; below that the N-split GEMM + LayerNorm pair has the lower latency
   // (bs=1: 1.67 ms vs 1.93 ms p50).  "fuse_ln" bit 2 forces it for any M (tests).
-  const bool big = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M >= 2 * e->lo.sm_count || (e->fuse_ln & 4);
+  const int Mr = (regime_batch > B ? regime_batch : B) * T;
+  const bool big = (Mr + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M >= 2 * e->lo.sm_count || (e->fuse_ln & 4);
   const bool fuse_proj = (e->fuse_ln & 1) && gemm_ln_supported(D) && big;
   const bool fuse_fc2 = (e->fuse_ln & 2) && gemm_ln_supported(D) && big;
   bool final_done = false;
@@ -1028,10 +1033,15 @@ int ar_decode(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int
 // One super-chunk (B <= max_batch images): `main` encodes everything (in `chunk`-image pieces) and projects the cross
 // K/V of the whole super-chunk; then the decoder - a latency-bound chain of small kernels - runs as ceil(B/dec_chunk)
 // independent chains on their own streams, concurrently (event fork/join, capturable into a CUDA graph).
+// part 0: the whole super-chunk.  part 1 / 2 (host entry points, PARSeq only): the encoder of images [0, split) alone /
+// the encoder of images [split, B) and everything after it - two graphs, so that the second half of the input is still
+// uploading while the first half is being encoded.
 int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B, int L, const void* images, bool u8,
-                  float* logits, int* ids_out, int* steps) {
+                  float* logits, int* ids_out, int* steps, int part = 0, int split = 0) {
   const long long img_sz = 3ll * e->cfg.img_h * e->cfg.img_w * (u8 ? 1 : 4);   // bytes per image
   const int D = e->D, T = e->T;
+  if (part == 1)
+    return encode_chunk(e, images, u8, split, e->mem, nullptr, e->main, true, B);
   if (e->arch == 1) {               // ViTSTR: encoder blocks, then norm + head on the kept token rows of each chunk
     for (int o = 0; o < B; o += e->chunk) {
       const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
@@ -1040,9 +1050,14 @@ int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B,
     }
     return PARSEQ_OK;
   }
-  for (int o = 0; o < B; o += e->chunk) {
-    const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
-    PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
+  if (part == 2) {
+    PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + split * img_sz, u8, B - split, e->mem + 1ll * split * T * D, nullptr,
+                        e->main, true, B));
+  } else {
+    for (int o = 0; o < B; o += e->chunk) {
+      const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
+      PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
+    }
   }
   // cross-attention K/V of the image memory, once per image (the reference recomputes it in every decode call)
   e->cur_cat = CAT_DEC_GEMM;
@@ -1088,8 +1103,8 @@ int num_steps_of(const parseq_engine* e, int max_length) {
 }
 
 // Replays (capturing on first use) the CUDA graph of one super-chunk of Bc images on the static I/O buffers.
-int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L, bool u8) {
-  std::vector<int> key = {Bc, L, a->max_length < 0 ? 1 : 0, a->decode_ar ? 1 : 0, a->refine_iters, u8 ? 1 : 0};
+int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L, bool u8, int part = 0, int split = 0) {
+  std::vector<int> key = {Bc, L, a->max_length < 0 ? 1 : 0, a->decode_ar ? 1 : 0, a->refine_iters, u8 ? 1 : 0, part, split};
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     parseq_forward_args aa = *a;
@@ -1099,7 +1114,7 @@ int run_graph(parseq_engine* e, const parseq_forward_args* a, int Bc, int L, boo
     const long long before = e->launches;
     PQ_CUDA(cudaStreamBeginCapture(e->main, cudaStreamCaptureModeThreadLocal));
     int r = forward_super(e, &aa, 0, Bc, L, u8 ? static_cast<const void*>(e->in_images_u8) : static_cast<const void*>(e->in_images),
-                          u8, e->out_logits, e->out_ids, e->out_steps);
+                          u8, e->out_logits, e->out_ids, e->out_steps, part, split);
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->main, &g);
     if (r != PARSEQ_OK) { if (g) cudaGraphDestroy(g); return r; }
@@ -1139,6 +1154,25 @@ int forward_impl(parseq_engine* e, const parseq_forward_args* a, const void* ima
     if (eager && !host) {
       PQ_TRY(forward_super(e, a, b0, Bc, L, images + b0 * img_sz, u8, logits + 1ll * b0 * L * e->C,
                            ids ? ids + 1ll * b0 * L : nullptr, e->out_steps));
+      continue;
+    }
+    if (host && !eager && e->arch == 0 && Bc >= 256 && e->chunk >= Bc) {
+      // upload in two halves on the copy stream; the encoder of the first half (its own graph) runs under the second upload
+      const int split = ((Bc / 2 + 7) / 8) * 8;
+      PQ_CUDA(cudaEventRecord(e->ev_c[2], e->main));                       // previous work on `main` (and the caller's stream)
+      PQ_CUDA(cudaStreamWaitEvent(e->copy, e->ev_c[2], 0));
+      PQ_CUDA(cudaMemcpyAsync(in_static, images + b0 * img_sz, static_cast<size_t>(split * img_sz), kin, e->copy));
+      PQ_CUDA(cudaEventRecord(e->ev_c[0], e->copy));
+      PQ_CUDA(cudaMemcpyAsync(static_cast<char*>(in_static) + split * img_sz, images + (b0 + split) * img_sz,
+                              static_cast<size_t>((Bc - split) * img_sz), kin, e->copy));
+      PQ_CUDA(cudaEventRecord(e->ev_c[1], e->copy));
+      PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_c[0], 0));
+      PQ_TRY(run_graph(e, a, Bc, L, u8, 1, split));
+      PQ_CUDA(cudaStreamWaitEvent(e->main, e->ev_c[1], 0));
+      PQ_TRY(run_graph(e, a, Bc, L, u8, 2, split));
+      PQ_CUDA(cudaMemcpyAsync(logits + 1ll * b0 * L * e->C, e->out_logits, static_cast<size_t>(1ll * Bc * L * e->C) * 4, kout,
+                              e->main));
+      if (ids) PQ_CUDA(cudaMemcpyAsync(ids + 1ll * b0 * L, e->out_ids, static_cast<size_t>(1ll * Bc * L) * 4, kout, e->main));
       continue;
     }
     PQ_CUDA(cudaMemcpyAsync(in_static, images + b0 * img_sz, static_cast<size_t>(Bc * img_sz), kin, e->main));
@@ -1296,6 +1330,9 @@ int parseq_create(const parseq_config* cfg, parseq_engine** out) {
   if (r == PARSEQ_OK) r = dev_alloc(&e->qs, 1ll * e->L * D);
   if (r == PARSEQ_OK) r = alloc_workspace(e);
   if (r == PARSEQ_OK && cudaStreamCreateWithFlags(&e->main, cudaStreamNonBlocking) != cudaSuccess) r = fail(PARSEQ_ERR_CUDA, "stream");
+  if (r == PARSEQ_OK && cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking) != cudaSuccess) r = fail(PARSEQ_ERR_CUDA, "stream");
+  for (int i = 0; i < 3 && r == PARSEQ_OK; ++i)
+    if (cudaEventCreateWithFlags(&e->ev_c[i], cudaEventDisableTiming) != cudaSuccess) r = fail(PARSEQ_ERR_CUDA, "event");
   if (r == PARSEQ_OK && (cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
                          cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess))
     r = fail(PARSEQ_ERR_CUDA, "event");
@@ -1314,6 +1351,8 @@ void parseq_destroy(parseq_engine* e) {
   if (e->qs) cudaFree(e->qs);
   free_workspace(e);
   if (e->main) cudaStreamDestroy(e->main);
+  if (e->copy) cudaStreamDestroy(e->copy);
+  for (auto ev : e->ev_c) if (ev) cudaEventDestroy(ev);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   for (auto& t : e->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }

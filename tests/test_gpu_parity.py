@@ -251,6 +251,33 @@ def test_cuda_graph_replay_equals_eager(B, ar, ri):
     assert torch.equal(lg, lg2) and torch.equal(ig, ig2)
 
 
+@pytest.mark.parametrize("B", [7, 300, 512, 700])
+def test_host_entry_points_equal_device_entry_points(B):
+    """parseq_forward_host / parseq_forward_host_u8 (pinned host buffers; from 256 images up the input is uploaded in two
+    halves and the first half is encoded - as its own CUDA graph - under the second upload; > max_batch: super-chunks) return
+    exactly what parseq_forward / parseq_forward_u8 return for the same images."""
+    from parseq_b200.weights import synth_images
+    cfg, sd, m = _model("parseq", 0)
+    eng = m.model.engine()
+    st = torch.cuda.current_stream().cuda_stream
+    x = synth_images(cfg, B, 88)
+    g = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (B, 32, 128, 3), dtype=torch.uint8, generator=g)
+    with torch.inference_mode():
+        ld, idd = m.model.forward(m.tokenizer, x.cuda(), None, return_ids=True)
+        lud = m(u8.cuda())
+    torch.cuda.synchronize()
+    hx, hu = x.pin_memory(), u8.pin_memory()
+    hl = torch.empty((B, 26, 95), dtype=torch.float32).pin_memory()
+    hi = torch.empty((B, 26), dtype=torch.int32).pin_memory()
+    hs = torch.empty((1,), dtype=torch.int32).pin_memory()
+    for _ in range(2):                      # capture, then replay
+        eng.forward_host(hx.data_ptr(), B, hl.data_ptr(), hi.data_ptr(), hs.data_ptr(), st, None, True, 1)
+        assert torch.equal(hl, ld.cpu()) and torch.equal(hi, idd.cpu())
+    eng.forward_u8(hu.data_ptr(), B, hl.data_ptr(), hi.data_ptr(), hs.data_ptr(), st, None, True, 1, host=True)
+    assert torch.equal(hl, lud.cpu())
+
+
 def test_two_engines_two_streams_one_device():
     """Two models (two engine handles, own streams / workspaces / options) interleaved on one device give the results
     they give alone; options are per handle (they used to be process globals)."""
