@@ -91,8 +91,6 @@ class ParseqConfig:
         return d
 
 
-_BASE = dict()
-
 PRESETS: Dict[str, Dict[str, Any]] = {
     # configs/model/parseq.yaml
     "parseq": dict(name="parseq"),
