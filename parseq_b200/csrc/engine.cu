@@ -347,7 +347,22 @@ int layernorm_launch(const LaunchOpts& lo, const float* x, const float* g, const
 
 int enc_attention_launch(const LaunchOpts& lo, const void* qkv, int B, int T, int D, int heads, void* out, cudaStream_t st) {
   if (D != heads * pq::ATT_DH) return fail(PARSEQ_ERR_UNSUPPORTED, "encoder attention kernels cover head_dim=64");
-  if (T != pq::ATT_T) {   // general token count: masked two-pass mma.sync kernel
+  if (T != pq::ATT_T && lo.attn_impl == 1 && T <= 256) {   // general token count on tcgen05: 3D maps [image][token][channel]
+    static bool attr_set2 = false;
+    if (!attr_set2) {
+      PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::atc2_smem_bytes<1>()));
+      PQ_CUDA(cudaFuncSetAttribute(pq::enc_attention_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::atc2_smem_bytes<2>()));
+      attr_set2 = true;
+    }
+    CUtensorMap tq, to;
+    PQ_TRY(make_tmap3d(&tq, qkv, 3ll * D, T, B, 3ll * D, 3ll * D * T, 64, 128));
+    PQ_TRY(make_tmap3d(&to, out, D, T, B, D, 1ll * D * T, 64, 32));
+    const dim3 grid(static_cast<unsigned>(B * heads), static_cast<unsigned>((T + 127) / 128));
+    if (T <= 128)
+      return launch_k(lo, pq::enc_attention_tc2_kernel<1>, grid, dim3(pq::ATC_THREADS), pq::atc2_smem_bytes<1>(), st, tq, to, D, heads, T);
+    return launch_k(lo, pq::enc_attention_tc2_kernel<2>, grid, dim3(pq::ATC_THREADS), pq::atc2_smem_bytes<2>(), st, tq, to, D, heads, T);
+  }
+  if (T != pq::ATT_T) {   // attn_impl = 0: masked two-pass mma.sync kernel (reference implementation of the unit tests)
     return launch_k(lo, pq::enc_attention_any_kernel, dim3(B * heads, (T + pq::ATT_T - 1) / pq::ATT_T), dim3(256), 0, st,
                     reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), T, D, heads);
   }

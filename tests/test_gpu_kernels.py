@@ -243,10 +243,13 @@ def test_enc_attention(lib, B, heads, impl):
     assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err
 
 
-@pytest.mark.parametrize("B,heads,T", [(2, 6, 196), (3, 12, 240), (1, 3, 130), (2, 6, 64)])
-def test_enc_attention_any_token_count(lib, B, heads, T):
-    """Masked two-pass attention for geometries that do not fill one 128-row tile per image."""
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("B,heads,T", [(2, 6, 196), (3, 12, 240), (1, 3, 130), (2, 6, 64), (40, 6, 129), (2, 6, 256), (3, 3, 49)])
+def test_enc_attention_any_token_count(lib, B, heads, T, impl):
+    """Geometries that do not fill one 128-row tile per image: tcgen05 kernel with two key blocks and one CTA per
+    (image, head, 128-query tile) over 3D tensor maps, and the masked two-pass mma.sync kernel."""
     from parseq_b200.engine import check
+    check(lib, lib.parseq_set_option(None, b"attn_impl", impl))
     d = 64
     D = heads * d
     g = torch.Generator(device="cuda").manual_seed(B * 10 + heads + T)
@@ -260,4 +263,5 @@ def test_enc_attention_any_token_count(lib, B, heads, T):
     o = (e.bfloat16().float() @ v) / e.sum(-1, keepdim=True)
     ref = o.permute(0, 2, 1, 3).reshape(B * T, D)
     err = (out.float() - ref).abs().max().item()
+    check(lib, lib.parseq_set_option(None, b"attn_impl", 1))
     assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err
