@@ -42,6 +42,21 @@ def test_sass_is_blackwell_native():
     for body in fn:
         for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
             assert mnemonic in body, mnemonic
+    # the cluster-owned AR kernel: TMA loads into its ring, hardware cluster barriers, warp MMA (10 instantiations)
+    fn = [b for b in sass.split("Function : ")[1:] if "dec_ar2_kernel" in b.split("\n", 1)[0]]
+    assert len(fn) == 10                      # D in {192, 384} x MT in {1, 2} x cluster size {6, 8}, D = 768 x {6, 8}
+    for body in fn:
+        for mnemonic in ("UTMALDG", "UCGABAR", "HMMA", "LDSM"):
+            assert mnemonic in body, mnemonic
+    # tcgen05 attention for T = 128 and the two-key-block variant for any T <= 256
+    fn = [b for b in sass.split("Function : ")[1:] if "enc_attention_tc" in b.split("\n", 1)[0]]
+    assert len(fn) == 3
+    for body in fn:
+        for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+            assert mnemonic in body, mnemonic
+    # the fc1 epilogue evaluates GELU on packed fp32 pairs
+    fn = [b for b in sass.split("Function : ")[1:] if "gemm_bf16_tcgen05_kernel" in b.split("\n", 1)[0]]
+    assert fn and all("FFMA2" in body for body in fn)
 
 
 def test_no_cpu_fallback():
