@@ -246,8 +246,12 @@ int gemm_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, lon
   PQ_TRY(ensure_sm_count(lo));
   // Tile choice from tests/bench_gemm.py on B200 (profiles/r1_gemm_microbench*.txt): single-CTA 128 x 256 tiles win
   // for the wide projections (QKV 1152 -> 4.5 tiles, fc1 1536), 128 x 192 for N = 384 / 768 (no padded columns),
-  // 128 x 128 for the small decoder GEMMs; the CTA-pair variant (cta_group::2) is correct but slower with this pipeline depth, so it is opt-in.
-  int CG = 1;
+  // 128 x 128 for the small decoder GEMMs.
+  // CTA pairs (cta_group::2: each CTA holds half of the W tile) win once the main loop is long enough to amortise the
+  // pair's per-tile handshakes: measured (profiles/r2_gemm_cta_pair_sweep.txt) 0.81 - 0.98x the single-CTA time for
+  // K >= 768 (D = 768 configs, unfused fc2), 1.05 - 1.21x for K = 384.  The accumulation order per output element is the
+  // same, so the choice does not change a single bit of the result (test_cta_pair_rows_equal_single_cta_rows).
+  int CG = (K >= 768 && M >= 1024) ? 2 : 1;
   if (lo.cta_group) CG = lo.cta_group;
   int BN;
   if (CG == 2) BN = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : 128;

@@ -275,7 +275,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     prefetch_tmap(&tmB);
     if (p.tma_out) prefetch_tmap(&tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], CG);        // leader's arrive.expect_tx (+ the peer producer's remote arrive)
+      mbar_init(&full_bar[s], 1);         // the leader's arrive.expect_tx covers the bytes of BOTH CTAs' loads
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -311,9 +311,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
           } else {
+            // Both CTAs' loads complete on the LEADER's barrier; only the leader arrives (expecting the bytes of both).
+            // The peer must not arrive remotely per stage: `mbarrier.arrive.release.cluster` on a remote barrier costs
+            // the producer thread a cluster-scope release (~700 cycles) per k-block and paced the whole pair at half
+            // speed (ncu: same tensor-busy cycles, twice the wall time - profiles/r2_ncu_cta_pair_gemm.txt).  The peer
+            // only refills a stage after the leader's multicast commit, i.e. after the previous phase of the leader's
+            // barrier has completed, so its complete_tx can never land in the wrong phase.
             const uint32_t leader_full = mapa_cluster(smem_u32(&full_bar[stage]), 0u);
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::kStageBytes);
-            else mbar_arrive_cluster(leader_full);
             tma_load_2d_pair(sa, &tmA, leader_full, kb * GEMM_BLOCK_K, m0);
             tma_load_2d_pair(sb, &tmB, leader_full, kb * GEMM_BLOCK_K, n0);
           }

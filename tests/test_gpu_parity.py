@@ -278,6 +278,21 @@ def test_host_entry_points_equal_device_entry_points(B):
     assert torch.equal(hl, lud.cpu())
 
 
+def test_cta_pair_rows_equal_single_cta_rows():
+    """GEMMs with K >= 768 and >= 1024 rows run on CTA pairs (cta_group::2); the same images in a batch small enough for
+    the single-CTA tiles, or with the pair forced off, give identical bits (D = 768 config, encoder output)."""
+    from parseq_b200.weights import synth_images
+    cfg, sd, m = _model("parseq-base-48x160", 4)
+    x = synth_images(cfg, 8, 5).cuda()
+    with torch.inference_mode():
+        mem8 = m.model.encode(x)                    # M = 8 * 240 = 1920 rows: pairs
+        mem2 = m.model.encode(x[2:4])               # 480 rows: single CTAs
+        m.model.set_engine_option("cta_group", 1)
+        mem8s = m.model.encode(x)
+    assert torch.equal(mem8, mem8s)
+    assert torch.equal(mem8[2:4], mem2)
+
+
 def test_two_engines_two_streams_one_device():
     """Two models (two engine handles, own streams / workspaces / options) interleaved on one device give the results
     they give alone; options are per handle (they used to be process globals)."""
