@@ -55,7 +55,8 @@ struct GemmCfg {
   // Shared memory is what bounds the TMA pipeline depth, so the widest tile trades epilogue buffering for a 4th
   // operand stage: BLOCK_N = 256 keeps ONE staging slab per epilogue warp (the previous store's smem read is
   // hidden behind the next chunk's TMEM load + math) and ONE bias slice shared by all epilogue warps.
-  static constexpr int kSlabs = (BLOCK_N == 256) ? 1 : 2;           // staging slabs (32 rows x 128 B) per epilogue warp
+  // (a CTA of a pair stages only half of W per k-block: its ring has room for two slabs per warp at every width)
+  static constexpr int kSlabs = (BLOCK_N == 256 && CG == 1) ? 1 : 2;   // staging slabs (32 rows x 128 B) per epilogue warp
   static constexpr bool kSharedBias = (BLOCK_N == 256);
   static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * kSlabs * 4096;
   static constexpr int kBiasBytes = (kSharedBias ? 1 : GEMM_EPI_WARPS) * BLOCK_N * 4;  // bias slice of the current tile
@@ -280,7 +281,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CG);  // one elected lane per epilogue warp of every CTA of the group
+      // leader: its own 8 epilogue warps + ONE forwarded arrival for the peer's 8; peer: collects its 8 warps locally
+      mbar_init(&tempty_bar[s], (CG == 2 && rank == 0) ? GEMM_EPI_WARPS + 1 : GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -327,6 +329,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
+    if (CG == 2 && rank != 0) {
+      // ===================== peer CTA: forward "accumulator stage drained" to the leader =====================
+      // The peer's epilogue warps arrive on their LOCAL barrier; this idle warp turns each completed phase into one
+      // remote arrival on the leader's barrier, so that no epilogue warp pays a cluster-scope release per tile.
+      if (lane == 0) {
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+          mbar_wait(&tempty_bar[as], aphase);
+          mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[as]), 0u));
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+      }
+    }
     // ===================== MMA issuer (single thread of the leader CTA) =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M * CG, BLOCK_N);
@@ -406,8 +422,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                     // 8*CG warp arrivals free this accumulator stage (leader's barrier)
-        if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[as]), 0u));
-        else mbar_arrive(&tempty_bar[as]);
+        mbar_arrive(&tempty_bar[as]);      // local (the peer's arrivals are forwarded by its otherwise idle warp 1)
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
