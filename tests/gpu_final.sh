@@ -1,9 +1,7 @@
 #!/bin/bash
-# Round-end style validation: full GPU test suite, smoke, default bench, the side benches that feed DESIGN.md section 6.
+# Round-end style validation: full GPU test suite, smoke, default bench.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/ -x -q -m gpu --timeout 600 2>&1 | tail -5
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
-timeout 600 python bench.py 2>gpurun_out/bench.err | tee gpurun_out/bench_final.json | cut -c1-400
+timeout 1500 python -m pytest tests/ -x -q -m gpu --timeout 900 2>&1 | tail -5 | tee gpurun_out/r2_final_tests.txt
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/r2_final_smoke.txt
+timeout 900 python bench.py 2>gpurun_out/bench.err | tee gpurun_out/r2_bench_final_n1.json | cut -c1-300
 tail -2 gpurun_out/bench.err
-timeout 300 python tests/bench_vitstr.py 2>&1 | tail -3
-timeout 600 python tests/bench_configs.py 2>&1 | tail -12
