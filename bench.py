@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--attn-impl", type=int, default=-1, help="encoder attention: 1 tcgen05 (default), 0 mma.sync")
     ap.add_argument("--ar-kernel", type=int, default=-1, help="AR loop: 2 cluster kernel (default), 1 grid-barrier kernel, 0 separate kernels")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM tile: 0 auto, 1 single CTA, 2 CTA pair")
+    ap.add_argument("--ln-cta-group", type=int, default=0, help="fused GEMM+LN tile: 0 auto, 1 single CTA, 2 CTA pair")
+    ap.add_argument("--pair-pdl", type=int, default=-1, help="experiments: PDL attribute on CTA-pair launches")
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -367,6 +369,10 @@ def main():
         opts["fuse_ln"] = args.fuse_ln
     if args.cta_group:
         opts["cta_group"] = args.cta_group
+    if args.ln_cta_group:
+        opts["ln_cta_group"] = args.ln_cta_group
+    if args.pair_pdl >= 0:
+        opts["pair_pdl"] = args.pair_pdl
     if args.block_n:
         opts["block_n"] = args.block_n
     cfg, sd, model = build_model("parseq", dev, True, 1, opts)

@@ -110,6 +110,8 @@ struct LaunchOpts {
   bool use_pdl = true;          // programmatic dependent launch on every kernel of the forward chain
   int block_n = 0;              // 0 = auto
   int cta_group = 0;            // 0 = auto, 1 / 2 = forced (tests)
+  int ln_cta_group = 0;         // same for the fused GEMM + LayerNorm kernel
+  bool pair_pdl = false;        // experiments: programmatic dependent launch also on CTA-pair (cluster) launches
   bool no_tma_epilogue = false; // tests: force the direct-store epilogue
   int gemm_stages = 0;          // experiments: cap the operand ring depth (0 = full)
   int attn_impl = 1;            // 1: tcgen05 kernel (attn_tc.cuh), 0: mma.sync kernel (kernels.cuh)
@@ -167,7 +169,7 @@ int launch_gemm_cfg(const LaunchOpts& lo, const CUtensorMap& ta, const CUtensorM
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (lo.use_pdl && CG == 1) ? 2 : 1;
+  cfg.numAttrs = (lo.use_pdl && (CG == 1 || lo.pair_pdl)) ? 2 : 1;
   PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return PARSEQ_OK;
 }
@@ -226,8 +228,10 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ln_head_argmax_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192>::kSmemBytes));
-  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192, 1>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 1>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192, 2>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 2>::kSmemBytes));
   PQ_TRY((warm_gemm_cfg<64, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 1>()));
   PQ_TRY((warm_gemm_cfg<192, 1>()));
@@ -305,11 +309,11 @@ int gemm_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, lon
 
 // x[M, D] += A[M, K] * W[D, K]^T + bias (fp32, in place); xn[M, D] = bf16(LayerNorm(x; gamma, beta, eps))   (gemm_ln.cuh)
 bool gemm_ln_supported(int D) { return D == 192 || D == 384; }
-template <int D>
+template <int D, int CG>
 int launch_gemm_ln(const LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int K, float* x,
                    const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
-  using Cfg = pq::GemmLnCfg<D>;
-  auto kern = pq::gemm_ln_fused_kernel<D>;
+  using Cfg = pq::GemmLnCfg<D, CG>;
+  auto kern = pq::gemm_ln_fused_kernel<D, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -317,22 +321,51 @@ int launch_gemm_ln(const LaunchOpts& lo, const void* A, long long lda, const voi
   }
   CUtensorMap ta, tb, tx, tn;
   PQ_TRY(make_tmap(&ta, A, 2, M, K, lda, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
-  PQ_TRY(make_tmap(&tb, W, 2, D, K, ldw, pq::GEMM_BLOCK_K, Cfg::kNH));
+  PQ_TRY(make_tmap(&tb, W, 2, D, K, ldw, pq::GEMM_BLOCK_K, Cfg::kBRows));
   PQ_TRY(make_tmap(&tx, x, 4, M, D, D, 32, 32));
   PQ_TRY(make_tmap(&tn, xn, 2, M, D, D, 64, 32));
   pq::GemmLnParams p;
   p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
-  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
-  const int grid = p.num_m_tiles < lo.sm_count ? p.num_m_tiles : lo.sm_count;
-  return launch_k(lo, kern, dim3(grid), dim3(pq::GLN_THREADS), Cfg::kSmemBytes, st, ta, tb, tx, tn, p);
+  const int tile_m = pq::GEMM_BLOCK_M * CG;
+  p.num_m_tiles = (M + tile_m - 1) / tile_m;
+  const int max_groups = lo.sm_count / CG;
+  const int groups = p.num_m_tiles < max_groups ? p.num_m_tiles : max_groups;
+  if constexpr (CG == 1) {
+    return launch_k(lo, kern, dim3(groups), dim3(pq::GLN_THREADS), Cfg::kSmemBytes, st, ta, tb, tx, tn, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
+    cfg.blockDim = dim3(pq::GLN_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (lo.use_pdl && lo.pair_pdl) ? 2 : 1;
+    PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx, tn, p));
+    return PARSEQ_OK;
+  }
 }
 int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int D,
                    int K, float* x, const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
   if (M <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm_ln: empty problem");
   PQ_TRY(ensure_sm_count(lo));
   PQ_TRY(load_driver_api());
-  if (D == 384) return launch_gemm_ln<384>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
-  if (D == 192) return launch_gemm_ln<192>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  // CTA pairs stage 30 % fewer operand bytes per row, bit-identical results - and no gain (profiles/r2_gemm_ln_cta_pair.txt:
+  // fc2' 124.5 -> 123.7 us, proj' 64.8 -> 71.6 us): this kernel is not operand-ingest bound.  Opt-in ("ln_cta_group").
+  int CG = 1;
+  if (lo.ln_cta_group) CG = lo.ln_cta_group;
+  if (CG == 2) {
+    if (D == 384) return launch_gemm_ln<384, 2>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+    if (D == 192) return launch_gemm_ln<192, 2>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  }
+  if (D == 384) return launch_gemm_ln<384, 1>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
+  if (D == 192) return launch_gemm_ln<192, 1>(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
   return fail(PARSEQ_ERR_UNSUPPORTED, "gemm_ln: embed_dim must be 192 or 384 (full rows in 512 TMEM columns)");
 }
 
@@ -1075,7 +1108,9 @@ int forward_super(parseq_engine* e, const parseq_forward_args* a, int b0, int B,
   } else {
     for (int o = 0; o < B; o += e->chunk) {
       const int Bs = (B - o < e->chunk) ? (B - o) : e->chunk;
-      PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, e->mem + 1ll * o * T * D, nullptr, e->main));
+      // kernel regime (fused GEMM + LayerNorm or not) from the super-chunk, so that it does not depend on `chunk`
+      PQ_TRY(encode_chunk(e, static_cast<const char*>(images) + o * img_sz, u8, Bs, e->mem + 1ll * o * T * D, nullptr, e->main,
+                          true, B));
     }
   }
   // cross-attention K/V of the image memory, once per image (the reference recomputes it in every decode call)
@@ -1694,6 +1729,13 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     if (e) drop_graphs(e);
     return PARSEQ_OK;
   }
+  if (n == "ln_cta_group") {
+    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "ln_cta_group: 0 (auto) / 1 / 2");
+    lo.ln_cta_group = static_cast<int>(value);
+    if (e) drop_graphs(e);
+    return PARSEQ_OK;
+  }
+  if (n == "pair_pdl") { lo.pair_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "fuse_ln") {
     if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
     e->fuse_ln = static_cast<int>(value) & 7;

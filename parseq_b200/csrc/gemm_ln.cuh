@@ -18,6 +18,13 @@
 //       the two partial (mean, M2) of a row are combined through shared memory (Chan's parallel variance);
 //       pass 2 (64-column chunks): v is read back from TMEM, normalised, packed to bf16 and TMA-stored to xn.
 // Rounding points are those of the unfused pair (TMA reduce-add epilogue + layernorm_kernel): fp32 x, bf16 xn.
+//
+// CG = 2 (CTA pair, tcgen05 cta_group::2): the pair computes 256 rows; each CTA still owns 128 FULL rows (same epilogue,
+// statistics stay local) but stages only HALF of each W column half (D/4 rows of W per stage; UMMA 256 x D/2 x 16 reads B
+// from both CTAs), so a stage is 28 KB instead of 40 KB and the operand bytes per 128 rows drop by 30 % - the main loop of
+// the K = 1536 launch (fc2) is operand-ingest bound.  Same k order per output element: results are bit-identical to CG = 1.
+// Pair plumbing as in gemm.cuh: loads of both CTAs complete on the leader's barrier, multicast commits, the peer's idle
+// warp 1 forwards one "TMEM half drained" arrival per tile and half.
 #pragma once
 #include "gemm.cuh"
 
@@ -36,11 +43,13 @@ constexpr int GLN_EPI_WARPS = 8;
 constexpr int GLN_THREADS = 64 + 32 * GLN_EPI_WARPS;
 constexpr int GLN_SLABS = 3;          // x chunks in flight per epilogue warp
 
-template <int D>
+template <int D, int CG = 1>
 struct GemmLnCfg {
+  static_assert(CG == 1 || CG == 2, "CG");
   static constexpr int kNH = D / 2;                                   // columns accumulated per pass over K
+  static constexpr int kBRows = kNH / CG;                             // W rows this CTA stages per k-block
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;     // 16 KB
-  static constexpr int kBBytes = kNH * GEMM_BLOCK_K * 2;
+  static constexpr int kBBytes = kBRows * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabBytes = GLN_EPI_WARPS * GLN_SLABS * 4096;
   static constexpr int kParamBytes = 3 * D * 4 + 4 * 2 * 32 * 8;      // bias, gamma, beta; (mean, M2) exchange of the warp pairs
@@ -58,12 +67,12 @@ struct GemmLnCfg {
   static_assert(kMyChunks % GLN_SLABS == 0, "whole rounds of slabs per tile");
 };
 
-template <int D>
+template <int D, int CG = 1>
 __global__ void __launch_bounds__(GLN_THREADS, 1)
 gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmN,
                      const GemmLnParams p) {
-  using Cfg = GemmLnCfg<D>;
+  using Cfg = GemmLnCfg<D, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -83,6 +92,11 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int first_tile = blockIdx.x / CG;                // tiles of 128 * CG rows
+  const int tile_step = gridDim.x / CG;
+  constexpr int kTileRows = GEMM_BLOCK_M * CG;
+  const int row_off = static_cast<int>(rank) * GEMM_BLOCK_M;
 
   grid_dep_launch();
   if (warp == 0 && lane == 0) {
@@ -90,12 +104,16 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], GLN_EPI_WARPS);
-    mbar_init(&tempty_bar[1], GLN_EPI_WARPS);
+    // pair leader: its own 8 epilogue warps + one forwarded arrival for the peer's 8
+    mbar_init(&tempty_bar[0], (CG == 2 && rank == 0) ? GLN_EPI_WARPS + 1 : GLN_EPI_WARPS);
+    mbar_init(&tempty_bar[1], (CG == 2 && rank == 0) ? GLN_EPI_WARPS + 1 : GLN_EPI_WARPS);
     for (int i = 0; i < GLN_EPI_WARPS * GLN_SLABS; ++i) mbar_init(&x_bar[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   // bias / gamma / beta are weights (never written by a preceding kernel): stage them before the dependency wait
   for (int j = threadIdx.x; j < D; j += GLN_THREADS) {
     s_bias[j] = (p.bias != nullptr) ? __ldg(p.bias + j) : 0.0f;
@@ -103,7 +121,7 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     s_beta[j] = __ldg(p.beta + j);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_dep_wait();
@@ -113,27 +131,49 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-        const int m0 = tile * GEMM_BLOCK_M;
+      for (int tile = first_tile; tile < p.num_m_tiles; tile += tile_step) {
+        const int m0 = tile * kTileRows + row_off;
         for (int h = 0; h < 2; ++h) {
+          const int n0 = h * Cfg::kNH + static_cast<int>(rank) * Cfg::kBRows;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-            tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, h * Cfg::kNH);
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+              tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+            } else {
+              // both CTAs' loads complete on the leader's barrier; only the leader arrives (gemm.cuh explains why)
+              const uint32_t leader_full = mapa_cluster(smem_u32(&full_bar[stage]), 0u);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::kStageBytes);
+              tma_load_2d_pair(sa, &tmA, leader_full, kb * GEMM_BLOCK_K, m0);
+              tma_load_2d_pair(sa + Cfg::kABytes, &tmB, leader_full, kb * GEMM_BLOCK_K, n0);
+            }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, Cfg::kNH);
+    if (CG == 2 && rank != 0) {
+      // peer CTA: turn each completed local "TMEM half drained" phase into ONE remote arrival on the leader's barrier
+      if (lane == 0) {
+        uint32_t tphase = 0;
+        for (int tile = first_tile; tile < p.num_m_tiles; tile += tile_step) {
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&tempty_bar[h], tphase);
+            mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[h]), 0u));
+          }
+          tphase ^= 1u;
+        }
+      }
+    }
+    // ===================== MMA issuer (the leader CTA's) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileRows, Cfg::kNH);
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.num_m_tiles; tile += tile_step) {
         for (int h = 0; h < 2; ++h) {
           // the previous tile's rows have left this half of TMEM (pass 2 releases the low columns first, so the
           // MMAs of half 0 overlap the rest of the previous tile's pass 2)
@@ -147,13 +187,17 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint64_t adesc = make_desc_k_sw128(sa);
             const uint64_t bdesc = make_desc_k_sw128(sa + Cfg::kABytes);
 #pragma unroll
-            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
-              umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                        static_cast<uint32_t>((kb | k) != 0));
-            umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              const uint32_t acc = static_cast<uint32_t>((kb | k) != 0);
+              if constexpr (CG == 2)
+                umma_bf16_pair(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, acc);
+              else
+                umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, acc);
+            }
+            if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&tfull_bar[h]);
+          if constexpr (CG == 2) umma_commit_pair(&tfull_bar[h], 0x3); else umma_commit(&tfull_bar[h]);
         }
         tphase ^= 1u;
       }
@@ -169,8 +213,8 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t tphase = 0;
     uint32_t xround = 0;                               // slab-barrier phases completed before this tile
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, xround += Cfg::kRounds) {
-      const int row0 = tile * GEMM_BLOCK_M + quarter * 32;
+    for (int tile = first_tile; tile < p.num_m_tiles; tile += tile_step, xround += Cfg::kRounds) {
+      const int row0 = tile * kTileRows + row_off + quarter * 32;
       // every slab is free here (first tile, or bulk_wait_group_read<0> at the end of the previous tile)
       if (lane == 0) {
 #pragma unroll
@@ -306,10 +350,11 @@ gemm_ln_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // peer smem / barriers stay valid until all are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 

@@ -179,6 +179,34 @@ def test_gemm_ln_fused(lib, M, D, K):
     assert torch.equal(x, x2) and torch.equal(xn, xn2)                                       # deterministic
 
 
+@pytest.mark.parametrize("M,D,K", [(128, 384, 384), (129, 384, 1536), (300, 384, 384), (148 * 128 + 77, 384, 1536), (65536, 384, 1536),
+                                   (513, 192, 192), (2000, 192, 768)])
+def test_gemm_ln_cta_pair_equals_single_cta(lib, M, D, K):
+    """The fused GEMM + LayerNorm kernel on CTA pairs (cta_group::2, each CTA stages half of each W column half) returns
+    the bits of the single-CTA kernel: same k order per output element, same epilogue.  Ragged M: the last pair tile has
+    an empty second CTA / a partial first one."""
+    from parseq_b200.engine import check
+    g = torch.Generator(device="cuda").manual_seed(M + D + K + 1)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((D, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((D,), device="cuda", generator=g)
+    gamma = 1.0 + 0.1 * torch.randn((D,), device="cuda", generator=g)
+    beta = 0.05 * torch.randn((D,), device="cuda", generator=g)
+    x0 = torch.randn((M, D), device="cuda", generator=g)
+    out = {}
+    try:
+        for cg in (1, 2):
+            check(lib, lib.parseq_set_option(None, b"ln_cta_group", cg))
+            x = x0.clone()
+            out[cg] = (x, _gemm_ln(lib, A, W, bias, x, gamma, beta, 1e-6))
+    finally:
+        check(lib, lib.parseq_set_option(None, b"ln_cta_group", 0))
+    assert torch.equal(out[1][0], out[2][0])
+    assert torch.equal(out[1][1], out[2][1])
+    ref_x = x0 + (A.float() @ W.float().t() + bias)
+    assert (out[2][0] - ref_x).abs().max().item() <= 2e-4 * max(1.0, ref_x.abs().max().item())
+
+
 def test_gemm_ln_fused_matches_unfused_pair(lib):
     """Same rounding points as the TMA reduce-add GEMM epilogue followed by layernorm_kernel: x bit-identical."""
     from parseq_b200.engine import check

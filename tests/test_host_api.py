@@ -38,7 +38,7 @@ def test_sass_is_blackwell_native():
     # the fused residual-GEMM + LayerNorm kernel: UMMA + TMA load AND store + TMEM load AND store (the updated row is
     # parked in TMEM between its two epilogue passes)
     fn = [b for b in sass.split("Function : ")[1:] if "gemm_ln_fused_kernel" in b.split("\n", 1)[0]]
-    assert len(fn) == 2                       # D = 192 and D = 384
+    assert len(fn) == 4                       # D in {192, 384} x {single CTA, CTA pair}
     for body in fn:
         for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
             assert mnemonic in body, mnemonic
