@@ -177,6 +177,12 @@ int parseq_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, con
 int parseq_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                         int M, int D, int K, float* x_inout, const float* gamma, const float* beta,
                         float eps, void* xn_bf16, parseq_stream_t stream);
+/* The whole MLP of a timm Block + the LayerNorm that follows (x = x + fc2(GELU(fc1(norm2(x)))) ; next norm1(x)) in one
+ * kernel: x_inout[M, D] += GELU(xn[M, D] * W1[4D, D]^T + b1) * W2[D, 4D]^T + b2 (fp32, in place; the bf16 hidden activation
+ * stays on the SM), xn_out_bf16[M, D] = bf16(LayerNorm(x_inout; gamma, beta, eps)); xn_out_bf16 may alias xn.  D in {192, 384}. */
+int parseq_mlp_ln_bf16(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2,
+                       int M, int D, float* x_inout, const float* gamma, const float* beta, float eps,
+                       void* xn_out_bf16, parseq_stream_t stream);
 /* y = bf16(LayerNorm(x; gamma, beta, eps)), x fp32 [M, D]. */
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M,
                           int D, void* y_bf16, float* y_f32_or_null, parseq_stream_t stream);

@@ -20,6 +20,7 @@
 #include "dec_ar2.cuh"
 #include "attn_tc.cuh"
 #include "gemm_ln.cuh"
+#include "mlp_ln.cuh"
 
 namespace {
 
@@ -232,6 +233,8 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 1>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192, 2>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 2>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<192>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<384>::kSmemBytes));
   PQ_TRY((warm_gemm_cfg<64, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 1>()));
   PQ_TRY((warm_gemm_cfg<192, 1>()));
@@ -369,6 +372,39 @@ int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, 
   return fail(PARSEQ_ERR_UNSUPPORTED, "gemm_ln: embed_dim must be 192 or 384 (full rows in 512 TMEM columns)");
 }
 
+// x[M, D] += GELU(xn W1^T + b1) W2^T + b2 (fp32, in place); xn_out = bf16(LayerNorm(x; gamma, beta, eps))   (mlp_ln.cuh)
+template <int D>
+int launch_mlp_ln(const LaunchOpts& lo, const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, int M,
+                  float* x, const float* gamma, const float* beta, float eps, void* xn_out, cudaStream_t st) {
+  using Cfg = pq::MlpLnCfg<D>;
+  auto kern = pq::mlp_ln_fused_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap txn, tw1, tw2, tx, tn;
+  PQ_TRY(make_tmap(&txn, xn, 2, M, D, D, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
+  PQ_TRY(make_tmap(&tw1, W1, 2, Cfg::kH, D, D, pq::GEMM_BLOCK_K, 64));
+  PQ_TRY(make_tmap(&tw2, W2, 2, D, Cfg::kH, Cfg::kH, pq::GEMM_BLOCK_K, Cfg::kNH));
+  PQ_TRY(make_tmap(&tx, x, 4, M, D, D, 32, 32));
+  PQ_TRY(make_tmap(&tn, xn_out, 2, M, D, D, 64, 32));
+  pq::MlpLnParams p;
+  p.M = M; p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
+  const int grid = p.num_m_tiles < lo.sm_count ? p.num_m_tiles : lo.sm_count;
+  return launch_k(lo, kern, dim3(grid), dim3(pq::MLP_THREADS), Cfg::kSmemBytes, st, txn, tw1, tw2, tx, tn, p);
+}
+int mlp_ln_launch(LaunchOpts& lo, const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, int M, int D,
+                  float* x, const float* gamma, const float* beta, float eps, void* xn_out, cudaStream_t st) {
+  if (M <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "mlp_ln: empty problem");
+  PQ_TRY(ensure_sm_count(lo));
+  PQ_TRY(load_driver_api());
+  if (D == 384) return launch_mlp_ln<384>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st);
+  if (D == 192) return launch_mlp_ln<192>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st);
+  return fail(PARSEQ_ERR_UNSUPPORTED, "mlp_ln: embed_dim must be 192 or 384 (hidden width 4 * embed_dim)");
+}
+
 int layernorm_launch(const LaunchOpts& lo, const float* x, const float* g, const float* b, float eps, int M, int D, void* y, float* y32,
                      cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   const int rows_per_block = 8;
@@ -468,6 +504,7 @@ struct parseq_engine {
   int ar_last_per = 0, ar_last_ncl = 0;
   int ar_cs = 0;                    // option "ar_cluster_size": 0 = auto, 6 / 8 = forced
   int ar_clusters_override = 0;     // option "ar_clusters": clusters the AR kernel spreads a batch over (0 = derived)
+  int fuse_mlp = 0;                 // fc1 + GELU + fc2 + residual + LayerNorm in one kernel (mlp_ln.cuh) where fuse_ln bit 1 applies
   int fuse_ln = 3;                  // bit 0: attn.proj, bit 1: mlp.fc2 also produce the LayerNorm that follows (gemm_ln.cuh)
   __nv_bfloat16 *ar_sa = nullptr, *ar_ca = nullptr, *ar_hd = nullptr;
   float *ar_y = nullptr, *ar_qc = nullptr, *ar_part = nullptr;
@@ -629,6 +666,13 @@ int gemm_ln(parseq_engine* e, const void* A, long long lda, const std::string& l
   return gemm_ln_launch(e->lo, A, lda, e->w(lin + ".weight"), K, e->wf(lin + ".bias"), M, e->D, K, x, e->wf(ln_prefix + ".weight"),
                         e->wf(ln_prefix + ".bias"), eps, y, st);
 }
+// x += fc2(GELU(fc1(xn)));  y = bf16(LayerNorm(x; <ln_prefix>))  in one kernel (block prefix `blk`, e.g. "encoder.blocks.3.")
+int mlp_ln(parseq_engine* e, const void* xn, const std::string& blk, int M, float* x, const std::string& ln_prefix, float eps,
+           void* y, cudaStream_t st) {
+  TimedScope ts(e, st, CAT_ENC_GEMM_LN, 4.0 * M * e->D * e->Me);
+  return mlp_ln_launch(e->lo, xn, e->w(blk + "mlp.fc1.weight"), e->wf(blk + "mlp.fc1.bias"), e->w(blk + "mlp.fc2.weight"),
+                       e->wf(blk + "mlp.fc2.bias"), M, e->D, x, e->wf(ln_prefix + ".weight"), e->wf(ln_prefix + ".bias"), eps, y, st);
+}
 int layernorm(parseq_engine* e, const float* x, const std::string& prefix, float eps, int M, void* y, float* y32,
               cudaStream_t st, const float* add = nullptr, int add_mod = 1, float* xw = nullptr) {
   TimedScope ts(e, st, CAT_LN, 0.0);
@@ -685,6 +729,7 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
   const bool big = (Mr + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M >= 2 * e->lo.sm_count || (e->fuse_ln & 4);
   const bool fuse_proj = (e->fuse_ln & 1) && gemm_ln_supported(D) && big;
   const bool fuse_fc2 = (e->fuse_ln & 2) && gemm_ln_supported(D) && big;
+  const bool fuse_mlp = e->fuse_mlp && fuse_fc2 && e->Me == 4 * D;
   bool final_done = false;
   for (int i = 0; i < e->cfg.enc_depth; ++i) {
     const std::string p = "encoder.blocks." + std::to_string(i) + ".";
@@ -702,6 +747,16 @@ int encode_chunk(parseq_engine* e, const void* images_any, bool u8, int B, __nv_
       PQ_TRY(gemm(e, e->att, D, e->w(p + "attn.proj.weight"), D, e->wf(p + "attn.proj.bias"), M, D, D, pq::EPI_F32, 1.0f,
                   e->x, D, 0, e->x, D, st));
       PQ_TRY(layernorm(e, e->x, p + "norm2", 1e-6f, M, e->xn, nullptr, st));
+    }
+    if (fuse_mlp && (!last || (final_norm && memory32 == nullptr))) {
+      // the whole MLP + the next LayerNorm in one kernel: the hidden activation never leaves the SM (mlp_ln.cuh)
+      if (!last) {
+        PQ_TRY(mlp_ln(e, e->xn, p, M, e->x, "encoder.blocks." + std::to_string(i + 1) + ".norm1", 1e-6f, e->xn, st));
+      } else {
+        PQ_TRY(mlp_ln(e, e->xn, p, M, e->x, "encoder.norm", 1e-6f, mem_out, st));
+        final_done = true;
+      }
+      continue;
     }
     PQ_TRY(gemm(e, e->xn, D, e->w(p + "mlp.fc1.weight"), D, e->wf(p + "mlp.fc1.bias"), M, e->Me, D, pq::EPI_GELU_BF16,
                 1.0f, nullptr, 0, 0, e->hid, e->Me, st));
@@ -1736,6 +1791,12 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     return PARSEQ_OK;
   }
   if (n == "pair_pdl") { lo.pair_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
+  if (n == "fuse_mlp") {
+    if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
+    e->fuse_mlp = value != 0 ? 1 : 0;
+    drop_graphs(e);
+    return PARSEQ_OK;
+  }
   if (n == "fuse_ln") {
     if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
     e->fuse_ln = static_cast<int>(value) & 7;
@@ -1833,6 +1894,11 @@ int parseq_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, 
                          float* x_inout, const float* gamma, const float* beta, float eps, void* xn_bf16,
                          parseq_stream_t stream) {
   return gemm_ln_launch(g_default_opts, A, lda, W, ldw, bias, M, D, K, x_inout, gamma, beta, eps, xn_bf16, reinterpret_cast<cudaStream_t>(stream));
+}
+int parseq_mlp_ln_bf16(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, int M, int D,
+                       float* x_inout, const float* gamma, const float* beta, float eps, void* xn_out_bf16, parseq_stream_t stream) {
+  return mlp_ln_launch(g_default_opts, xn, W1, b1, W2, b2, M, D, x_inout, gamma, beta, eps, xn_out_bf16,
+                       reinterpret_cast<cudaStream_t>(stream));
 }
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y_bf16,
                           float* y_f32_or_null, parseq_stream_t stream) {

@@ -207,6 +207,55 @@ def test_gemm_ln_cta_pair_equals_single_cta(lib, M, D, K):
     assert (out[2][0] - ref_x).abs().max().item() <= 2e-4 * max(1.0, ref_x.abs().max().item())
 
 
+def _mlp_ln(lib, xn, W1, b1, W2, b2, x, gamma, beta, eps, out=None):
+    from parseq_b200.engine import check
+    M, D = xn.shape
+    xo = torch.empty((M, D), dtype=torch.bfloat16, device=xn.device) if out is None else out
+    check(lib, lib.parseq_mlp_ln_bf16(xn.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, D, x.data_ptr(),
+                                      gamma.data_ptr(), beta.data_ptr(), eps, xo.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    return xo
+
+
+@pytest.mark.parametrize("M,D", [(128, 384), (300, 384), (77, 384), (148 * 128 * 2 + 77, 384), (65536, 384), (513, 192), (20000, 192)])
+def test_mlp_ln_fused_equals_two_kernels(lib, M, D):
+    """fc1 + GELU + fc2 + residual + LayerNorm in one kernel (mlp_ln.cuh; the hidden activation stays on the SM) returns
+    the bits of the two-kernel path (GEMM with the GELU epilogue, then the fused residual-GEMM + LayerNorm): same k order
+    per output element, same rounding points (bf16 hidden, fp32 x, bf16 xn).  Also in place (xn_out aliases xn), and against
+    an fp32 torch restatement of the block's MLP (modules: timm Mlp + Block residual + LayerNorm)."""
+    H = 4 * D
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    xn = torch.randn((M, D), device="cuda", generator=g).bfloat16()
+    W1 = (torch.randn((H, D), device="cuda", generator=g) * 0.06).bfloat16()
+    b1 = 0.2 * torch.randn((H,), device="cuda", generator=g)
+    W2 = (torch.randn((D, H), device="cuda", generator=g) * 0.04).bfloat16()
+    b2 = 0.2 * torch.randn((D,), device="cuda", generator=g)
+    gamma = 1.0 + 0.1 * torch.randn((D,), device="cuda", generator=g)
+    beta = 0.05 * torch.randn((D,), device="cuda", generator=g)
+    x0 = torch.randn((M, D), device="cuda", generator=g)
+    # two kernels
+    hid = torch.empty((M, H), dtype=torch.bfloat16, device="cuda")
+    _gemm(lib, xn, W1, b1, 2, out=hid)
+    xa = x0.clone()
+    xna = _gemm_ln(lib, hid, W2, b2, xa, gamma, beta, 1e-6)
+    # one kernel
+    xb = x0.clone()
+    xnb = _mlp_ln(lib, xn, W1, b1, W2, b2, xb, gamma, beta, 1e-6)
+    assert torch.equal(xa, xb), (xa - xb).abs().max().item()
+    assert torch.equal(xna, xnb)
+    # in place: the normalised rows overwrite the kernel's own input
+    xc = x0.clone()
+    buf = xn.clone()
+    _mlp_ln(lib, buf, W1, b1, W2, b2, xc, gamma, beta, 1e-6, out=buf)
+    assert torch.equal(xc, xb) and torch.equal(buf, xnb)
+    # fp32 restatement (hidden rounded to bf16 like every implementation that stores it)
+    h32 = torch.nn.functional.gelu(xn.float() @ W1.float().t() + b1).bfloat16().float()
+    ref_x = x0 + (h32 @ W2.float().t() + b2)
+    assert (xb - ref_x).abs().max().item() <= 2e-3 * max(1.0, ref_x.abs().max().item())
+    ref_n = torch.nn.functional.layer_norm(xb, (D,), gamma, beta, 1e-6)
+    assert ((xnb.float() - ref_n).abs() <= 2.0 ** -8 * ref_n.abs() + 1e-5).all()
+
+
 def test_gemm_ln_fused_matches_unfused_pair(lib):
     """Same rounding points as the TMA reduce-add GEMM epilogue followed by layernorm_kernel: x bit-identical."""
     from parseq_b200.engine import check
