@@ -183,6 +183,10 @@ int parseq_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, 
 int parseq_mlp_ln_bf16(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2,
                        int M, int D, float* x_inout, const float* gamma, const float* beta, float eps,
                        void* xn_out_bf16, parseq_stream_t stream);
+/* Same with cycle counters of CTA 0 (16 x uint64, device) for tests/prof_mlp_ln.py. */
+int parseq_mlp_ln_bf16_prof(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2,
+                            int M, int D, float* x_inout, const float* gamma, const float* beta, float eps,
+                            void* xn_out_bf16, unsigned long long* prof_dev, parseq_stream_t stream);
 /* y = bf16(LayerNorm(x; gamma, beta, eps)), x fp32 [M, D]. */
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M,
                           int D, void* y_bf16, float* y_f32_or_null, parseq_stream_t stream);

@@ -112,6 +112,7 @@ struct LaunchOpts {
   int block_n = 0;              // 0 = auto
   int cta_group = 0;            // 0 = auto, 1 / 2 = forced (tests)
   int ln_cta_group = 0;         // same for the fused GEMM + LayerNorm kernel
+  int mlp_cta_group = 0;        // one-kernel MLP (mlp_ln.cuh): 0 = auto (pairs), 1 / 2 = forced
   bool pair_pdl = false;        // experiments: programmatic dependent launch also on CTA-pair (cluster) launches
   bool no_tma_epilogue = false; // tests: force the direct-store epilogue
   int gemm_stages = 0;          // experiments: cap the operand ring depth (0 = full)
@@ -233,8 +234,10 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 1>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192, 2>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 2>::kSmemBytes));
-  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<192>::kSmemBytes));
-  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<384>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<192, 1>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<384, 1>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<192, 2>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<384, 2>::kSmemBytes));
   PQ_TRY((warm_gemm_cfg<64, 1>()));
   PQ_TRY((warm_gemm_cfg<128, 1>()));
   PQ_TRY((warm_gemm_cfg<192, 1>()));
@@ -373,11 +376,11 @@ int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, 
 }
 
 // x[M, D] += GELU(xn W1^T + b1) W2^T + b2 (fp32, in place); xn_out = bf16(LayerNorm(x; gamma, beta, eps))   (mlp_ln.cuh)
-template <int D>
+template <int D, int CG>
 int launch_mlp_ln(const LaunchOpts& lo, const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, int M,
-                  float* x, const float* gamma, const float* beta, float eps, void* xn_out, cudaStream_t st) {
-  using Cfg = pq::MlpLnCfg<D>;
-  auto kern = pq::mlp_ln_fused_kernel<D>;
+                  float* x, const float* gamma, const float* beta, float eps, void* xn_out, cudaStream_t st, unsigned long long* prof) {
+  using Cfg = pq::MlpLnCfg<D, CG>;
+  auto kern = pq::mlp_ln_fused_kernel<D, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -385,23 +388,51 @@ int launch_mlp_ln(const LaunchOpts& lo, const void* xn, const void* W1, const fl
   }
   CUtensorMap txn, tw1, tw2, tx, tn;
   PQ_TRY(make_tmap(&txn, xn, 2, M, D, D, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
-  PQ_TRY(make_tmap(&tw1, W1, 2, Cfg::kH, D, D, pq::GEMM_BLOCK_K, 64));
-  PQ_TRY(make_tmap(&tw2, W2, 2, D, Cfg::kH, Cfg::kH, pq::GEMM_BLOCK_K, Cfg::kNH));
+  PQ_TRY(make_tmap(&tw1, W1, 2, Cfg::kH, D, D, pq::GEMM_BLOCK_K, Cfg::kW1Rows));
+  PQ_TRY(make_tmap(&tw2, W2, 2, D, Cfg::kH, Cfg::kH, pq::GEMM_BLOCK_K, Cfg::kW2Rows));
   PQ_TRY(make_tmap(&tx, x, 4, M, D, D, 32, 32));
   PQ_TRY(make_tmap(&tn, xn_out, 2, M, D, D, 64, 32));
   pq::MlpLnParams p;
-  p.M = M; p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
-  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
-  const int grid = p.num_m_tiles < lo.sm_count ? p.num_m_tiles : lo.sm_count;
-  return launch_k(lo, kern, dim3(grid), dim3(pq::MLP_THREADS), Cfg::kSmemBytes, st, txn, tw1, tw2, tx, tn, p);
+  p.M = M; p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps; p.prof = prof;
+  const int tile_m = pq::GEMM_BLOCK_M * CG;
+  p.num_m_tiles = (M + tile_m - 1) / tile_m;
+  const int max_groups = lo.sm_count / CG;
+  const int groups = p.num_m_tiles < max_groups ? p.num_m_tiles : max_groups;
+  if constexpr (CG == 1) {
+    return launch_k(lo, kern, dim3(groups), dim3(pq::MLP_THREADS), Cfg::kSmemBytes, st, txn, tw1, tw2, tx, tn, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(groups * CG));
+    cfg.blockDim = dim3(pq::MLP_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (lo.use_pdl && lo.pair_pdl) ? 2 : 1;
+    PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, txn, tw1, tw2, tx, tn, p));
+    return PARSEQ_OK;
+  }
 }
 int mlp_ln_launch(LaunchOpts& lo, const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, int M, int D,
-                  float* x, const float* gamma, const float* beta, float eps, void* xn_out, cudaStream_t st) {
+                  float* x, const float* gamma, const float* beta, float eps, void* xn_out, cudaStream_t st,
+                  unsigned long long* prof = nullptr) {
   if (M <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "mlp_ln: empty problem");
   PQ_TRY(ensure_sm_count(lo));
   PQ_TRY(load_driver_api());
-  if (D == 384) return launch_mlp_ln<384>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st);
-  if (D == 192) return launch_mlp_ln<192>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st);
+  // CTA pairs stage half of every weight box per CTA: the same ring covers twice as many k-steps (mlp_ln.cuh)
+  const int CG = lo.mlp_cta_group ? lo.mlp_cta_group : 2;
+  if (CG == 2) {
+    if (D == 384) return launch_mlp_ln<384, 2>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st, prof);
+    if (D == 192) return launch_mlp_ln<192, 2>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st, prof);
+  }
+  if (D == 384) return launch_mlp_ln<384, 1>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st, prof);
+  if (D == 192) return launch_mlp_ln<192, 1>(lo, xn, W1, b1, W2, b2, M, x, gamma, beta, eps, xn_out, st, prof);
   return fail(PARSEQ_ERR_UNSUPPORTED, "mlp_ln: embed_dim must be 192 or 384 (hidden width 4 * embed_dim)");
 }
 
@@ -1790,6 +1821,12 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
     if (e) drop_graphs(e);
     return PARSEQ_OK;
   }
+  if (n == "mlp_cta_group") {
+    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "mlp_cta_group: 0 (auto) / 1 / 2");
+    lo.mlp_cta_group = static_cast<int>(value);
+    if (e) drop_graphs(e);
+    return PARSEQ_OK;
+  }
   if (n == "pair_pdl") { lo.pair_pdl = value != 0; if (e) drop_graphs(e); return PARSEQ_OK; }
   if (n == "fuse_mlp") {
     if (e == nullptr) return fail(PARSEQ_ERR_INVALID_ARG, "null engine");
@@ -1899,6 +1936,13 @@ int parseq_mlp_ln_bf16(const void* xn, const void* W1, const float* b1, const vo
                        float* x_inout, const float* gamma, const float* beta, float eps, void* xn_out_bf16, parseq_stream_t stream) {
   return mlp_ln_launch(g_default_opts, xn, W1, b1, W2, b2, M, D, x_inout, gamma, beta, eps, xn_out_bf16,
                        reinterpret_cast<cudaStream_t>(stream));
+}
+// same, with 16 cycle counters of CTA 0 written to `prof_dev` (tests/prof_mlp_ln.py; see mlp_ln.cuh for the slots)
+int parseq_mlp_ln_bf16_prof(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, int M, int D,
+                            float* x_inout, const float* gamma, const float* beta, float eps, void* xn_out_bf16,
+                            unsigned long long* prof_dev, parseq_stream_t stream) {
+  return mlp_ln_launch(g_default_opts, xn, W1, b1, W2, b2, M, D, x_inout, gamma, beta, eps, xn_out_bf16,
+                       reinterpret_cast<cudaStream_t>(stream), prof_dev);
 }
 int parseq_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y_bf16,
                           float* y_f32_or_null, parseq_stream_t stream) {

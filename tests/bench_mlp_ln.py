@@ -36,6 +36,10 @@ def run(M, D):
     print(f"M={M:6d} D={D} | one kernel {tf:7.1f} us ({fl/tf/1e6:6.1f} TF/s) | fc1 {t1:6.1f} + fc2/LN {t2:6.1f} = {t1+t2:7.1f} us "
           f"({fl/(t1+t2)/1e6:6.1f} TF/s)", flush=True)
 
-for M in (148 * 128, 65536, 148 * 128 * 4):
-    run(M, 384)
-run(65536, 192)
+for cg, pdl in ((1, 0), (2, 0), (2, 1)):
+    check(lib, lib.parseq_set_option(None, b"mlp_cta_group", cg))
+    check(lib, lib.parseq_set_option(None, b"pair_pdl", pdl))
+    print(f"--- one kernel: mlp_cta_group={cg} pair_pdl={pdl}", flush=True)
+    for M in (148 * 128, 65536, 148 * 128 * 4):
+        run(M, 384)
+    run(65536, 192)

@@ -217,8 +217,17 @@ def _mlp_ln(lib, xn, W1, b1, W2, b2, x, gamma, beta, eps, out=None):
     return xo
 
 
-@pytest.mark.parametrize("M,D", [(128, 384), (300, 384), (77, 384), (148 * 128 * 2 + 77, 384), (65536, 384), (513, 192), (20000, 192)])
-def test_mlp_ln_fused_equals_two_kernels(lib, M, D):
+@pytest.fixture(params=[1, 2], ids=["single-cta", "cta-pair"])
+def mlp_cta_group(request, lib):
+    from parseq_b200.engine import check
+    check(lib, lib.parseq_set_option(None, b"mlp_cta_group", request.param))
+    yield request.param
+    check(lib, lib.parseq_set_option(None, b"mlp_cta_group", 0))
+
+
+@pytest.mark.parametrize("M,D", [(128, 384), (129, 384), (256, 384), (300, 384), (77, 384), (148 * 128 * 2 + 77, 384), (65536, 384), (513, 192),
+                                 (20000, 192)])
+def test_mlp_ln_fused_equals_two_kernels(lib, mlp_cta_group, M, D):
     """fc1 + GELU + fc2 + residual + LayerNorm in one kernel (mlp_ln.cuh; the hidden activation stays on the SM) returns
     the bits of the two-kernel path (GEMM with the GELU epilogue, then the fused residual-GEMM + LayerNorm): same k order
     per output element, same rounding points (bf16 hidden, fp32 x, bf16 xn).  Also in place (xn_out aliases xn), and against
