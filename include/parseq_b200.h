@@ -149,9 +149,12 @@ int64_t parseq_debug_int(parseq_engine* e, const char* name);
  * for parseq_get_timing; 0: off + clear), "block_n" (engine-independent GEMM tile override, tests), "fuse_ln" (bit 0: the attention-projection GEMM, bit 1: the fc2 GEMM
  * also produces the LayerNorm that follows it, used when the batch fills the machine at least twice with 128-row tiles; bit 2:
  * for any batch; default 3; 0: separate LayerNorm kernels), "ar_kernel" (AR loop: 2 = cluster-owned persistent kernel,
- * default; 1 = grid-barrier persistent kernel; 0 = chain of separate kernels), "attn_impl", "cta_group", "gemm_stages",
- * "tma_epilogue" (kernel-variant switches for tests).  Options are PER HANDLE; with e == NULL the launch options
- * (block_n, attn_impl, pdl, tma_epilogue, gemm_stages, cta_group) set the process defaults that the stand-alone kernel
+ * default; 1 = grid-barrier persistent kernel; 0 = chain of separate kernels), "fuse_mlp" (1: fc1 + GELU + fc2 + residual +
+ * LayerNorm of an encoder block in one kernel where fuse_ln bit 1 applies - bit-identical results, slower on B200, default 0),
+ * "attn_impl", "cta_group" / "ln_cta_group" / "mlp_cta_group" (0 auto, 1 single CTA, 2 CTA pair: GEMM / fused GEMM+LayerNorm /
+ * one-kernel MLP), "pair_pdl", "gemm_stages", "tma_epilogue" (kernel-variant switches for tests).  Options are PER HANDLE; with
+ * e == NULL the launch options (block_n, attn_impl, pdl, tma_epilogue, gemm_stages, cta_group, ln_cta_group, mlp_cta_group,
+ * pair_pdl) set the process defaults that the stand-alone kernel
  * entry points below use and that handles created afterwards inherit. */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of
