@@ -142,17 +142,20 @@ struct A2Ring {
   uint64_t* full;
   const DecAr2Maps* maps;
   int rank, n_own, img0, per_here;     // img0: first image of the cluster
+  int hs_row, hs_kb;                   // head-split mode (few images per cluster): this CTA's (row, k-block) unit, or hs_row < 0
   int tbox, tb, T;
   int items_per_step, total;
   int seg_b, seg_c, seg_d, seg_e, seg_f, seg_g;   // first item index of each segment
   int cons, prod;
 
+  // n_kv_units: (image, k-block) cross-attention units of this CTA: n_own * KT, or 0 / 1 in head-split mode
   __device__ void init(uint8_t* slots_, uint64_t* full_, const DecAr2Maps* maps_, int rank_, int n_own_, int img0_, int tbox_,
-                       int tb_, int T_, int steps) {
+                       int tb_, int T_, int steps, int n_kv_units, int hs_row_, int hs_kb_) {
     slots = slots_; full = full_; maps = maps_; rank = rank_; n_own = n_own_; img0 = img0_; tbox = tbox_; tb = tb_; T = T_;
+    hs_row = hs_row_; hs_kb = hs_kb_;
     seg_b = Cfg::NSL_S;
     seg_c = 2 * Cfg::NSL_S;
-    seg_d = seg_c + n_own * 2 * Cfg::KT * tb;
+    seg_d = seg_c + n_kv_units * 2 * tb;
     seg_e = seg_d + Cfg::NSL_S;
     seg_f = seg_e + Cfg::NCH1 * Cfg::KT;
     seg_g = seg_f + Cfg::NCH2 * Cfg::KT2;
@@ -175,10 +178,14 @@ struct A2Ring {
     if (it < seg_d) {                    // K/V boxes: (own image, K|V, k-block, key block)
       int j = it - seg_c;
       const int t = j % tb; j /= tb;
-      const int kb = j % Cfg::KT; j /= Cfg::KT;
-      const int kv = j & 1;
-      const int oi = j >> 1;
-      const int img = img0 + rank + CS * oi;
+      int kb, kv, img;
+      if (hs_row >= 0) {                 // head-split: one (image, k-block) unit: K boxes, then V boxes
+        kb = hs_kb; kv = j & 1; img = img0 + hs_row;
+      } else {
+        kb = j % Cfg::KT; j /= Cfg::KT;
+        kv = j & 1;
+        img = img0 + rank + CS * (j >> 1);
+      }
       mbar_expect_tx(bar, static_cast<uint32_t>(tbox * 128));
       // column-blocked cache [2D/64][rows][64], row = image * T + key: one contiguous tbox x 128 B run (rows past the
       // image's T keys belong to the next image or are out of bounds: masked by the softmax)
@@ -265,7 +272,9 @@ __device__ __forceinline__ void mma_box(float (&acc)[NTW][4], const uint8_t* ati
   }
 }
 
-template <int D, int MT, int CS>
+// HS: head-split cross-attention (launch-wide: rows per cluster x k-blocks <= cluster size; see below).  A template flag
+// so that the throughput instantiations carry none of its registers / branches.
+template <int D, int MT, int CS, bool HS = false>
 __global__ void __launch_bounds__(A2_LAUNCH_THREADS, 1)
 dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
   using Cfg = A2Cfg<D, MT, CS>;
@@ -316,8 +325,15 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
     const int r = i >> 5, c = i & 31;
     s_ids[i] = (r < nrows) ? p.ids[static_cast<long long>(img0 + r) * p.ids_ld + c] : 0;
   }
+  // Head-split cross-attention: with so few images that (images x 64-channel k-blocks) fit the cluster, every CTA takes ONE
+  // (image, k-block = head pair) unit instead of whole images - at bs = 1 six CTAs stream one K and one V panel each instead of
+  // one CTA streaming twelve.  Per head the arithmetic and its order are unchanged (same bits as the image-split path).
+  constexpr bool hs = HS;                                            // (the host launches HS only if p.per * KT <= CS)
+  const int hs_row = (hs && rank < nrows * KT) ? rank / KT : -1;
+  const int hs_kb = hs ? rank % KT : 0;
+  const int c_own = hs ? (hs_row >= 0 ? 1 : 0) : n_own;             // cross-attention passes of this CTA
   A2Ring<D, MT, CS> ring;
-  ring.init(s_ring, s_bar, &maps, rank, n_own, img0, p.tbox, p.tb, p.T, p.L);
+  ring.init(s_ring, s_bar, &maps, rank, n_own, img0, p.tbox, p.tb, p.T, p.L, hs ? c_own : n_own * KT, hs ? hs_row : -1, hs_kb);
   __syncthreads();
   cluster_sync_relacq();              // every CTA of the cluster is running (remote stores are legal) and zero-filled
 
@@ -536,10 +552,19 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           const int cg = rank * DS + nt * 8 + 2 * t;
           const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bq_c + cg));
           const int r0 = mi * 16 + g, r1 = r0 + 8;
-          st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r0 / CS) * D + cg]), static_cast<uint32_t>(r0 % CS)),
-                         (acc[j][0] + bb.x) * p.qscale, (acc[j][1] + bb.y) * p.qscale);
-          st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r1 / CS) * D + cg]), static_cast<uint32_t>(r1 % CS)),
-                         (acc[j][2] + bb.x) * p.qscale, (acc[j][3] + bb.y) * p.qscale);
+          if (hs) {                      // the 64-column block goes to the CTA that owns (row, k-block)
+            if (r0 < nrows)
+              st_cluster_v2f(mapa_cluster(smem_u32(&s_q[cg]), static_cast<uint32_t>(r0 * KT + (cg >> 6))),
+                             (acc[j][0] + bb.x) * p.qscale, (acc[j][1] + bb.y) * p.qscale);
+            if (r1 < nrows)
+              st_cluster_v2f(mapa_cluster(smem_u32(&s_q[cg]), static_cast<uint32_t>(r1 * KT + (cg >> 6))),
+                             (acc[j][2] + bb.x) * p.qscale, (acc[j][3] + bb.y) * p.qscale);
+          } else {
+            st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r0 / CS) * D + cg]), static_cast<uint32_t>(r0 % CS)),
+                           (acc[j][0] + bb.x) * p.qscale, (acc[j][1] + bb.y) * p.qscale);
+            st_cluster_v2f(mapa_cluster(smem_u32(&s_q[(r1 / CS) * D + cg]), static_cast<uint32_t>(r1 % CS)),
+                           (acc[j][2] + bb.x) * p.qscale, (acc[j][3] + bb.y) * p.qscale);
+          }
         }
       }
     }
@@ -551,11 +576,12 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
       const int ntk = p.tbox >> 6;                    // n8 tiles of keys per warp inside a key block (tbox / 8 warps / 8)
       const int kw = ntk * 8;                         // keys per warp per block
       A2_PROF4(0);
-      for (int oi = 0; oi < n_own; ++oi) {
-        const int r = rank + CS * oi;
+      const int kb_lo = hs ? hs_kb : 0, kb_hi = hs ? hs_kb + 1 : KT;      // k-blocks (head pairs) this CTA computes per pass
+      for (int oi = 0; oi < c_own; ++oi) {
+        const int r = hs ? hs_row : rank + CS * oi;
         const float* qrow = s_q + oi * D;
         // the query's A-operand words, split into bf16 hi + lo (q = hi + lo to ~16 mantissa bits), once per image
-        for (int i = tid; i < KT * 16; i += A2_THREADS) {
+        for (int i = kb_lo * 16 + tid; i < kb_hi * 16; i += A2_THREADS) {
           const float* qd = qrow + (i >> 2) * 16 + 2 * (i & 3);        // (kb, ks) = i / 4, thread-in-quad t = i % 4
           const float q0 = qd[0], q1 = qd[1], q8 = qd[8], q9 = qd[9];
           const float h0 = __bfloat162float(__float2bfloat16_rn(q0)), h1 = __bfloat162float(__float2bfloat16_rn(q1));
@@ -575,7 +601,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
               slo[a][b][c][0] = slo[a][b][c][1] = slo[a][b][c][2] = slo[a][b][c][3] = 0.f;
             }
         // ---- S = Q_blockdiag K^T: K box kb holds dims [64 kb, 64 kb + 64) = heads 2 kb, 2 kb + 1 ----
-        for (int kb = 0; kb < KT; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
 #pragma unroll
           for (int tbi = 0; tbi < 2; ++tbi) {
             if (tbi < p.tb) {
@@ -697,7 +723,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           const int prow = (lane & 7) + ((lane >> 3) & 1) * 8;
           uint32_t ph[2][4], pl[2][4];                         // [key block][frag]
           int cur_mh = -1;
-          for (int kb = 0; kb < KT; ++kb) {
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
             const int mh = (2 * kb) >> 4;
             if (mh != cur_mh) {                                // (re)load this warp's P fragments for the m16 tile of heads
               cur_mh = mh;
@@ -746,7 +772,7 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           }
           a2_csync();
           // sum the 8 key slices (fixed order), normalise by the row sum of the head, round to bf16
-          for (int i = tid; i < D / 2; i += A2_THREADS) {
+          for (int i = kb_lo * 32 + tid; i < kb_hi * 32; i += A2_THREADS) {
             const int d0 = 2 * i, hh = d0 >> 5;
             float tot = 0.f;
 #pragma unroll
@@ -762,7 +788,8 @@ dec_ar2_kernel(const __grid_constant__ DecAr2Maps maps, const DecAr2Params p) {
           }
         }
         a2_csync();
-        for (int ch = tid; ch < D / 8; ch += A2_THREADS) bcast16(s_a2, r, ch * 8, *reinterpret_cast<const uint4*>(&s_ca[ch * 8]));
+        for (int ch = kb_lo * 8 + tid; ch < kb_hi * 8; ch += A2_THREADS)
+          bcast16(s_a2, r, ch * 8, *reinterpret_cast<const uint4*>(&s_ca[ch * 8]));
         if (oi < 4) A2_PROF4(3 + 3 * oi);
       }
     }

@@ -208,6 +208,9 @@ template <int D, int MT, int CS>
 int ar2_attr() {
   PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<D, MT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(pq::dec_ar2_smem_bytes<D, MT, CS>())));
+  if constexpr (MT == 1 && CS == 8 && D / 64 <= CS)      // head-split variant for tiny batches
+    PQ_CUDA(cudaFuncSetAttribute(pq::dec_ar2_kernel<D, MT, CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(pq::dec_ar2_smem_bytes<D, MT, CS>())));
   return PARSEQ_OK;
 }
 int ar2_set_attributes() {
@@ -1020,6 +1023,14 @@ int ar2_launch(parseq_engine* e, const pq::DecAr2Params& p, int ncl, cudaStream_
   cudaLaunchAttribute attr[1];
   ar2_config<D, MT, CS>(e, cfg, attr, ncl, st);
   e->ar_last_per = p.per; e->ar_last_ncl = ncl; e->ar_last_cs = CS;
+  if constexpr (MT == 1 && CS == 8 && D / 64 <= CS) {
+    // so few images per cluster that (images x head pairs) fit its CTAs: every CTA takes one (image, head pair) of the
+    // cross-attention instead of whole images (bs = 1: 9 -> 2.5 us per step; same bits per head)
+    if (p.per * (D / 64) <= CS) {
+      PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::dec_ar2_kernel<D, MT, CS, true>, e->ar2_maps[0], p));
+      return PARSEQ_OK;
+    }
+  }
   PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::dec_ar2_kernel<D, MT, CS>, e->ar2_maps[CS == 6 ? 1 : 0], p));
   return PARSEQ_OK;
 }

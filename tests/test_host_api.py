@@ -44,7 +44,7 @@ def test_sass_is_blackwell_native():
             assert mnemonic in body, mnemonic
     # the cluster-owned AR kernel: TMA loads into its ring, hardware cluster barriers, warp MMA (10 instantiations)
     fn = [b for b in sass.split("Function : ")[1:] if "dec_ar2_kernel" in b.split("\n", 1)[0]]
-    assert len(fn) == 10                      # D in {192, 384} x MT in {1, 2} x cluster size {6, 8}, D = 768 x {6, 8}
+    assert len(fn) == 12                      # D in {192, 384} x MT in {1, 2} x cluster size {6, 8}, D = 768 x {6, 8}, head-split D in {192, 384}
     for body in fn:
         for mnemonic in ("UTMALDG", "UCGABAR", "HMMA", "LDSM"):
             assert mnemonic in body, mnemonic
