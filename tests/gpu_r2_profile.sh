@@ -15,5 +15,9 @@ cap ar2 dec_ar2 "-c 1"
 cap gemm_ln gemm_ln_fused "-c 2"
 cap gemm gemm_bf16_tcgen05 "-s 1 -c 2"
 cap attn enc_attention_tc "-c 1"
+# the opt-in one-kernel MLP + LayerNorm inside the same step (single-CTA variant): what it does to the DRAM bytes of a block
+export PQ_FUSE_MLP=1 PQ_MLP_CTA_GROUP=1
+cap mlp_ln mlp_ln_fused "-c 1"
+unset PQ_FUSE_MLP PQ_MLP_CTA_GROUP
 ls -la gpurun_out/ | tail -20
 du -sh gpurun_out

@@ -11,6 +11,10 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 cfg = make_config("parseq")
 m = create_model("parseq", decode_ar=True, refine_iters=1)
 m.model.load_state_dict(init_state_dict(cfg, 0))
+if os.environ.get("PQ_FUSE_MLP"):        # opt-in one-kernel MLP + LayerNorm (mlp_ln.cuh), to capture its traffic inside a step
+    m.model.set_engine_option("fuse_mlp", 1)
+    if os.environ.get("PQ_MLP_CTA_GROUP"):
+        m.model.set_engine_option("mlp_cta_group", int(os.environ["PQ_MLP_CTA_GROUP"]))
 m = m.eval().to("cuda")
 x = synth_images(cfg, B, 1).cuda()
 with torch.inference_mode():

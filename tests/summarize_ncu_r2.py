@@ -55,7 +55,7 @@ def load(name, labels):
                 continue
             v = float(row[col[metric]].replace(",", ""))
             u = units[col[metric]]
-            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}.get(u, 1.0)
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(u, 1.0)
             d[key] = v * mult
         out.append(d)
     return out
@@ -64,6 +64,8 @@ inst += load("gemm", ["QKV (M=65536,N=1152,K=384)", "fc1+GELU (N=1536,K=384), FF
 inst += load("gemm_ln", ["attn.proj + residual + norm2 (K=384)", "mlp.fc2 + residual + next norm1 (K=1536)"])
 inst += load("ar2", ["whole AR loop: 26 steps, 512 images, 22 clusters of 6"])
 inst += load("attn", ["ViT attention core, 512 x 6 (image, head) CTAs"])
+if os.path.exists(os.path.join(G, "r2_raw_mlp_ln.csv")):
+    inst += load("mlp_ln", ["OPT-IN one-kernel MLP: fc1 + GELU + fc2 + residual + next norm1 (replaces fc1 + fc2 rows)"])
 def dram(d): return d.get("dram_read_bytes", 0.0) + d.get("dram_write_bytes", 0.0)
 traffic = {
     "source": "ncu --set full --clock-control none, tests/gpu_r2_profile.sh, bs=512 forward, encoder block 0 / AR loop (round 2 final build)",
