@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM tile: 0 auto, 1 single CTA, 2 CTA pair")
     ap.add_argument("--ln-cta-group", type=int, default=0, help="fused GEMM+LN tile: 0 auto, 1 single CTA, 2 CTA pair")
     ap.add_argument("--pair-pdl", type=int, default=-1, help="experiments: PDL attribute on CTA-pair launches")
+    ap.add_argument("--ln-split", type=int, default=-1, help="fused GEMM+LN: 2 = column-split CTA-pair kernel (gemm_ln2.cuh), 1 = full-row kernel")
     ap.add_argument("--fuse-mlp", type=int, default=-1, help="1: fc1 + GELU + fc2 + residual + LayerNorm in one kernel (mlp_ln.cuh)")
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -375,6 +376,8 @@ def main():
         opts["ln_cta_group"] = args.ln_cta_group
     if args.pair_pdl >= 0:
         opts["pair_pdl"] = args.pair_pdl
+    if args.ln_split >= 0:
+        opts["ln_split"] = args.ln_split
     if args.fuse_mlp >= 0:
         opts["fuse_mlp"] = args.fuse_mlp
     if args.block_n:

@@ -20,6 +20,7 @@
 #include "dec_ar2.cuh"
 #include "attn_tc.cuh"
 #include "gemm_ln.cuh"
+#include "gemm_ln2.cuh"
 #include "mlp_ln.cuh"
 
 namespace {
@@ -112,6 +113,7 @@ struct LaunchOpts {
   int block_n = 0;              // 0 = auto
   int cta_group = 0;            // 0 = auto, 1 / 2 = forced (tests)
   int ln_cta_group = 0;         // same for the fused GEMM + LayerNorm kernel
+  int ln_split = 0;             // fused GEMM + LayerNorm: 2 = column-split CTA-pair kernel (gemm_ln2.cuh), 0 / 1 = gemm_ln.cuh
   int mlp_cta_group = 0;        // one-kernel MLP (mlp_ln.cuh): 0 = auto (pairs), 1 / 2 = forced
   bool pair_pdl = false;        // experiments: programmatic dependent launch also on CTA-pair (cluster) launches
   bool no_tma_epilogue = false; // tests: force the direct-store epilogue
@@ -237,6 +239,7 @@ int init_kernel_attributes() {
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 1>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<192, 2>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_fused_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLnCfg<384, 2>::kSmemBytes));
+  PQ_CUDA(cudaFuncSetAttribute(pq::gemm_ln_split_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::GemmLn2Cfg<384>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<192, 1>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<384, 1>::kSmemBytes));
   PQ_CUDA(cudaFuncSetAttribute(pq::mlp_ln_fused_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pq::MlpLnCfg<192, 2>::kSmemBytes));
@@ -360,6 +363,44 @@ int launch_gemm_ln(const LaunchOpts& lo, const void* A, long long lda, const voi
     return PARSEQ_OK;
   }
 }
+// version 2 (gemm_ln2.cuh): the columns of a 128-row tile split over a CTA pair, double-buffered TMEM, statistics through DSMEM
+int launch_gemm_ln_split(const LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int K,
+                         float* x, const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
+  constexpr int D = 384;
+  using Cfg = pq::GemmLn2Cfg<D>;
+  auto kern = pq::gemm_ln_split_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb, tx, tn;
+  PQ_TRY(make_tmap(&ta, A, 2, M, K, lda, pq::GEMM_BLOCK_K, pq::GEMM_BLOCK_M));
+  PQ_TRY(make_tmap(&tb, W, 2, D, K, ldw, pq::GEMM_BLOCK_K, Cfg::kN));
+  PQ_TRY(make_tmap(&tx, x, 4, M, D, D, 32, 32));
+  PQ_TRY(make_tmap(&tn, xn, 2, M, D, D, 64, 32));
+  pq::GemmLnParams p;
+  p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.num_m_tiles = (M + pq::GEMM_BLOCK_M - 1) / pq::GEMM_BLOCK_M;
+  const int max_groups = lo.sm_count / 2;
+  const int groups = p.num_m_tiles < max_groups ? p.num_m_tiles : max_groups;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
+  cfg.blockDim = dim3(pq::GLN_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lo.use_pdl ? 2 : 1;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx, tn, p));
+  return PARSEQ_OK;
+}
 int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int D,
                    int K, float* x, const float* gamma, const float* beta, float eps, void* xn, cudaStream_t st) {
   if (M <= 0 || K <= 0) return fail(PARSEQ_ERR_INVALID_ARG, "gemm_ln: empty problem");
@@ -367,6 +408,11 @@ int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, 
   PQ_TRY(load_driver_api());
   // CTA pairs stage 30 % fewer operand bytes per row, bit-identical results - and no gain (profiles/r2_gemm_ln_cta_pair.txt:
   // fc2' 124.5 -> 123.7 us, proj' 64.8 -> 71.6 us): this kernel is not operand-ingest bound.  Opt-in ("ln_cta_group").
+  // The column-split pair kernel (gemm_ln2.cuh) pays where the MMAs of a tile are long enough to be worth hiding under the
+  // previous tile's epilogue: fc2 (K = 1536) 124.6 -> 110.7 us, attn.proj (K = 384) 64.8 -> 68.1 us
+  // (profiles/r2_gemm_ln_split_pair.txt).  ln_split: 0 auto (K >= 768), 1 never, 2 always (D = 384).
+  if (D == 384 && (lo.ln_split == 2 || (lo.ln_split == 0 && K >= 768 && M >= 1024)))
+    return launch_gemm_ln_split(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
   int CG = 1;
   if (lo.ln_cta_group) CG = lo.ln_cta_group;
   if (CG == 2) {
@@ -1829,6 +1875,12 @@ int parseq_set_option(parseq_engine* e, const char* name, int64_t value) {
   if (n == "ln_cta_group") {
     if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "ln_cta_group: 0 (auto) / 1 / 2");
     lo.ln_cta_group = static_cast<int>(value);
+    if (e) drop_graphs(e);
+    return PARSEQ_OK;
+  }
+  if (n == "ln_split") {
+    if (value < 0 || value > 2) return fail(PARSEQ_ERR_INVALID_ARG, "ln_split: 0 (auto) / 1 (off) / 2 (on)");
+    lo.ln_split = static_cast<int>(value);
     if (e) drop_graphs(e);
     return PARSEQ_OK;
   }

@@ -31,10 +31,11 @@ def run(M, K):
     tf, tg, tl = timeit(fused), timeit(gemm), timeit(ln)
     print(f"M={M:6d} K={K:5d} | fused {tf:7.1f} us ({2.0*M*D*K/tf/1e6:6.1f} TF/s) | gemm {tg:7.1f} + ln {tl:5.1f} = {tg+tl:7.1f} us", flush=True)
 
-for cg, pdl in ((1, 0), (2, 0), (2, 1)):
+for cg, pdl, split in ((1, 0, 1), (2, 0, 1), (1, 0, 2)):
     check(lib, lib.parseq_set_option(None, b"ln_cta_group", cg))
     check(lib, lib.parseq_set_option(None, b"pair_pdl", pdl))
-    print(f"--- fused kernel: ln_cta_group={cg} pair_pdl={pdl}", flush=True)
+    check(lib, lib.parseq_set_option(None, b"ln_split", split))
+    print(f"--- fused kernel: ln_cta_group={cg} pair_pdl={pdl} ln_split={split} (2 = column-split pair, gemm_ln2.cuh)", flush=True)
     for M in (65536, 148 * 128 * 4):
         for K in (384, 1536, 4096):
             run(M, K)

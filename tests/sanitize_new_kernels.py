@@ -21,6 +21,7 @@ for D, M in ((384, 300), (192, 513), (384, 148 * 128 + 77)):
     hid = torch.empty((M, H), dtype=torch.bfloat16, device="cuda")
     check(lib, lib.parseq_gemm_bf16(xn.data_ptr(), D, W1.data_ptr(), D, b1.data_ptr(), M, H, D, 2, 1.0, None, 0, 0, hid.data_ptr(), H, st))
     ref = {}
+    check(lib, lib.parseq_set_option(None, b"ln_split", 1))
     for cg in (1, 2):
         check(lib, lib.parseq_set_option(None, b"ln_cta_group", cg))
         x = x0.clone(); xo = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
@@ -29,6 +30,15 @@ for D, M in ((384, 300), (192, 513), (384, 148 * 128 + 77)):
         torch.cuda.synchronize()
         ref[cg] = (x, xo)
     assert torch.equal(ref[1][0], ref[2][0]) and torch.equal(ref[1][1], ref[2][1])
+    if D == 384:                                       # column-split pair kernel (gemm_ln2.cuh): x identical, xn within one bf16 ulp
+        check(lib, lib.parseq_set_option(None, b"ln_split", 2))
+        x = x0.clone(); xo = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
+        check(lib, lib.parseq_gemm_ln_bf16(hid.data_ptr(), H, W2.data_ptr(), H, b2.data_ptr(), M, D, H, x.data_ptr(), ga.data_ptr(),
+                                           be.data_ptr(), 1e-6, xo.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert torch.equal(x, ref[1][0])
+        assert (xo.float() - ref[1][1].float()).abs().max().item() <= 2.0 ** -7 * ref[1][1].float().abs().max().item()
+    check(lib, lib.parseq_set_option(None, b"ln_split", 1))
     for cg in (1, 2):
         check(lib, lib.parseq_set_option(None, b"mlp_cta_group", cg))
         x = x0.clone(); xo = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
@@ -37,4 +47,5 @@ for D, M in ((384, 300), (192, 513), (384, 148 * 128 + 77)):
         torch.cuda.synchronize()
         assert torch.equal(x, ref[1][0]) and torch.equal(xo, ref[1][1])
     print("ok: D", D, "M", M, "gemm_ln pair == single, mlp_ln (single, pair) == two kernels", flush=True)
+check(lib, lib.parseq_set_option(None, b"ln_split", 0))
 print("sanitize_new_kernels done")

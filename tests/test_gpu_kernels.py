@@ -151,9 +151,18 @@ def _gemm_ln(lib, A, W, bias, x, gamma, beta, eps):
     return xn
 
 
+@pytest.fixture(params=[1, 2], ids=["full-row-cta", "column-split-pair"])
+def ln_split(request, lib):
+    """gemm_ln.cuh (one CTA owns full rows) / gemm_ln2.cuh (the columns of a tile split over a CTA pair; D = 384 only)."""
+    from parseq_b200.engine import check
+    check(lib, lib.parseq_set_option(None, b"ln_split", request.param))
+    yield request.param
+    check(lib, lib.parseq_set_option(None, b"ln_split", 0))
+
+
 @pytest.mark.parametrize("M,D,K", [(128, 384, 384), (300, 384, 384), (4096, 384, 1536), (77, 384, 1536),
                                    (148 * 128 * 2 + 77, 384, 384), (65536, 384, 1536), (513, 192, 192), (2000, 192, 768)])
-def test_gemm_ln_fused(lib, M, D, K):
+def test_gemm_ln_fused(lib, ln_split, M, D, K):
     """x += A W^T + b (fp32 in place) and xn = bf16(LayerNorm(x)) in one kernel (gemm_ln.cuh) vs the same two ops in torch;
     ragged M, several tiles per CTA, both K of the encoder (attn.proj, mlp.fc2)."""
     g = torch.Generator(device="cuda").manual_seed(M + D + K)
@@ -195,12 +204,14 @@ def test_gemm_ln_cta_pair_equals_single_cta(lib, M, D, K):
     x0 = torch.randn((M, D), device="cuda", generator=g)
     out = {}
     try:
+        check(lib, lib.parseq_set_option(None, b"ln_split", 1))         # the full-row kernel, not the column-split one
         for cg in (1, 2):
             check(lib, lib.parseq_set_option(None, b"ln_cta_group", cg))
             x = x0.clone()
             out[cg] = (x, _gemm_ln(lib, A, W, bias, x, gamma, beta, 1e-6))
     finally:
         check(lib, lib.parseq_set_option(None, b"ln_cta_group", 0))
+        check(lib, lib.parseq_set_option(None, b"ln_split", 0))
     assert torch.equal(out[1][0], out[2][0])
     assert torch.equal(out[1][1], out[2][1])
     ref_x = x0 + (A.float() @ W.float().t() + bias)
@@ -265,7 +276,7 @@ def test_mlp_ln_fused_equals_two_kernels(lib, mlp_cta_group, M, D):
     assert ((xnb.float() - ref_n).abs() <= 2.0 ** -8 * ref_n.abs() + 1e-5).all()
 
 
-def test_gemm_ln_fused_matches_unfused_pair(lib):
+def test_gemm_ln_fused_matches_unfused_pair(lib, ln_split):
     """Same rounding points as the TMA reduce-add GEMM epilogue followed by layernorm_kernel: x bit-identical."""
     from parseq_b200.engine import check
     M, D, K = 3000, 384, 1536
