@@ -42,6 +42,11 @@ def test_sass_is_blackwell_native():
     for body in fn:
         for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
             assert mnemonic in body, mnemonic
+    # its column-split CTA-pair version: the same inside a cluster (hardware cluster barrier; the statistics go to the peer by distributed shared memory)
+    fn = [b for b in sass.split("Function : ")[1:] if "gemm_ln_split_kernel" in b.split("\n", 1)[0]]
+    assert len(fn) == 1
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UCGABAR"):
+        assert mnemonic in fn[0], mnemonic
     # the cluster-owned AR kernel: TMA loads into its ring, hardware cluster barriers, warp MMA (10 instantiations)
     fn = [b for b in sass.split("Function : ")[1:] if "dec_ar2_kernel" in b.split("\n", 1)[0]]
     assert len(fn) == 12                      # D in {192, 384} x MT in {1, 2} x cluster size {6, 8}, D = 768 x {6, 8}, head-split D in {192, 384}
