@@ -71,25 +71,68 @@ def load_peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (every 5 ms; the timed region of the
+    default run is ~130 ms - too short for a freshly started `nvidia-smi -lms`), `nvidia-smi` as the fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index: int):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
         self.path = f"/tmp/parseq_clocks_{os.getpid()}.csv"
 
+    def _poll(self):
+        import pynvml as N
+        h = self.handle
+        masks = [(N.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (N.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                 (N.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (N.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for m, n in masks:
+                    if r & m:
+                        self.reasons.add(n)
+                self.power.append(N.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def start(self):
+        try:
+            import pynvml as N
+            import threading
+            N.nvmlInit()
+            self.handle = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = [float(N.nvmlDeviceGetMaxClockInfo(self.handle, N.NVML_CLOCK_SM))]
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                       "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None, "source": "nvml"}
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -99,7 +142,6 @@ class ClockSampler:
             self.proc.kill()
         self.f.close()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
                 parts = [p.strip() for p in line.split(",")]
@@ -109,7 +151,7 @@ class ClockSampler:
                     sm.append(float(parts[0])); mx.append(float(parts[1]))
                 except ValueError:
                     continue
-                for n, v in zip(names, parts[3:7]):
+                for n, v in zip(self.NAMES, parts[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             os.remove(self.path)
@@ -117,7 +159,7 @@ class ClockSampler:
             pass
         if sm:
             out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                   "samples": len(sm), "source": "nvidia-smi"}
         return out
 
 

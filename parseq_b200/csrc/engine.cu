@@ -410,8 +410,9 @@ int gemm_ln_launch(LaunchOpts& lo, const void* A, long long lda, const void* W, 
   // fc2' 124.5 -> 123.7 us, proj' 64.8 -> 71.6 us): this kernel is not operand-ingest bound.  Opt-in ("ln_cta_group").
   // The column-split pair kernel (gemm_ln2.cuh) pays where the MMAs of a tile are long enough to be worth hiding under the
   // previous tile's epilogue: fc2 (K = 1536) 124.6 -> 110.7 us, attn.proj (K = 384) 64.8 -> 68.1 us
-  // (profiles/r2_gemm_ln_split_pair.txt).  ln_split: 0 auto (K >= 768), 1 never, 2 always (D = 384).
-  if (D == 384 && (lo.ln_split == 2 || (lo.ln_split == 0 && K >= 768 && M >= 1024)))
+  // (profiles/r2_gemm_ln_split_pair.txt).  ln_split: 0 auto (K >= 768), 1 never, 2 always (D = 384).  Where the fused kernels are
+  // used at all is decided by the caller from the batch regime (encode_chunk).
+  if (D == 384 && (lo.ln_split == 2 || (lo.ln_split == 0 && K >= 768)))   // by K only: a row's bits must not depend on the batch
     return launch_gemm_ln_split(lo, A, lda, W, ldw, bias, M, K, x, gamma, beta, eps, xn, st);
   int CG = 1;
   if (lo.ln_cta_group) CG = lo.ln_cta_group;

@@ -257,7 +257,12 @@ def test_mlp_ln_fused_equals_two_kernels(lib, mlp_cta_group, M, D):
     hid = torch.empty((M, H), dtype=torch.bfloat16, device="cuda")
     _gemm(lib, xn, W1, b1, 2, out=hid)
     xa = x0.clone()
-    xna = _gemm_ln(lib, hid, W2, b2, xa, gamma, beta, 1e-6)
+    from parseq_b200.engine import check
+    check(lib, lib.parseq_set_option(None, b"ln_split", 1))     # the full-row GEMM + LayerNorm kernel, whose epilogue mlp_ln.cuh shares
+    try:
+        xna = _gemm_ln(lib, hid, W2, b2, xa, gamma, beta, 1e-6)
+    finally:
+        check(lib, lib.parseq_set_option(None, b"ln_split", 0))
     # one kernel
     xb = x0.clone()
     xnb = _mlp_ln(lib, xn, W1, b1, W2, b2, xb, gamma, beta, 1e-6)
