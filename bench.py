@@ -663,7 +663,7 @@ def main():
     entries = [
         entry("enc_gemm", "tensor", "gemm_bf16_tcgen05_kernel (QKV, fc1+GELU, patch embedding)", tim["enc_gemm"]["flops"], "TFLOP/s",
               "avg_dram_bytes_per_launch"),
-        entry("enc_gemm_ln", "hbm", "gemm_ln_fused_kernel (attn.proj / mlp.fc2 + residual + following LayerNorm)",
+        entry("enc_gemm_ln", "hbm", "gemm_ln_fused_kernel (attn.proj) / gemm_ln_split_kernel (mlp.fc2): residual GEMM + the following LayerNorm",
               (fused_bytes(D_) + fused_bytes(D_ * cfg.enc_mlp_ratio)) * (n_fused / 2.0), "GB/s", "fused_avg_dram_bytes_per_launch"),
         entry("dec_ar", "hbm", "dec_ar2_kernel (whole AR loop: 26 steps; independent clusters of 6 / 8 CTAs, TMA producer warp)"
               if args.ar_kernel in (-1, 2) else "dec_ar_kernel (whole AR loop, grid barriers)",
