@@ -152,9 +152,10 @@ int64_t parseq_debug_int(parseq_engine* e, const char* name);
  * default; 1 = grid-barrier persistent kernel; 0 = chain of separate kernels), "fuse_mlp" (1: fc1 + GELU + fc2 + residual +
  * LayerNorm of an encoder block in one kernel where fuse_ln bit 1 applies - bit-identical results, slower on B200, default 0),
  * "attn_impl", "cta_group" / "ln_cta_group" / "mlp_cta_group" (0 auto, 1 single CTA, 2 CTA pair: GEMM / fused GEMM+LayerNorm /
- * one-kernel MLP), "pair_pdl", "gemm_stages", "tma_epilogue" (kernel-variant switches for tests).  Options are PER HANDLE; with
+ * one-kernel MLP), "ln_split" (fused GEMM+LayerNorm: 0 auto = the column-split CTA-pair kernel for K >= 768, 1 never, 2 always),
+ * "pair_pdl", "gemm_stages", "tma_epilogue" (kernel-variant switches for tests).  Options are PER HANDLE; with
  * e == NULL the launch options (block_n, attn_impl, pdl, tma_epilogue, gemm_stages, cta_group, ln_cta_group, mlp_cta_group,
- * pair_pdl) set the process defaults that the stand-alone kernel
+ * ln_split, pair_pdl) set the process defaults that the stand-alone kernel
  * entry points below use and that handles created afterwards inherit. */
 int parseq_set_option(parseq_engine* e, const char* name, int64_t value);
 /* After a synchronised forward with "timing"=1: device milliseconds, algorithmic FLOPs and launch count of

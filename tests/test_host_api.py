@@ -22,6 +22,25 @@ def test_library_exports_every_declared_symbol(lib):
     assert b"sm_100a" in lib.parseq_version()
 
 
+def test_launch_options_documented_in_the_header_are_accepted(lib):
+    """Every launch option the header names is accepted on the NULL handle (process defaults; no CUDA call involved), range
+    errors and unknown names are reported through the status code."""
+    from parseq_b200.engine import check
+    names = ["block_n", "attn_impl", "pdl", "tma_epilogue", "gemm_stages", "cta_group", "ln_cta_group", "mlp_cta_group", "pair_pdl",
+             "ln_split"]
+    hdr = open(os.path.join(ROOT, "include", "parseq_b200.h")).read()
+    for n in names:
+        assert f'"{n}"' in hdr or n in hdr, n
+        default = 1 if n in ("attn_impl", "pdl", "tma_epilogue") else 0
+        check(lib, lib.parseq_set_option(None, n.encode(), default))
+    for n, bad in (("cta_group", 3), ("ln_cta_group", -1), ("mlp_cta_group", 5), ("ln_split", 3), ("block_n", 100)):
+        assert lib.parseq_set_option(None, n.encode(), bad) != 0
+        assert lib.parseq_last_error()
+        check(lib, lib.parseq_set_option(None, n.encode(), 0))
+    assert lib.parseq_set_option(None, b"fuse_mlp", 1) != 0          # per-handle options need a handle
+    assert lib.parseq_set_option(None, b"no_such_option", 1) != 0
+
+
 def test_sass_is_blackwell_native():
     """The GEMM kernel must contain tcgen05 / TMA / TMEM instructions (UTCHMMA, UTMALDG, LDTM)."""
     import shutil
